@@ -1,0 +1,1168 @@
+// Stage C — batched variational-GP regions (sm_100a), float64.
+//
+// Replaces fit_gp_spp (/root/reference/gapro/gaussian_process_utils.py:382-445) and the gpytorch
+// machinery behind GPClassificationModel (:11-25); the arithmetic is SURVEY.md §8a-C, implemented
+// with the hand-derived gradient.  Every region's matrices are padded to multiples of 64 and live
+// in the caller's workspace; one training step is a fixed sequence of ragged, batched tile
+// kernels over ALL regions of a chunk (tile tables built on the host), so small and large regions
+// share launches and the 148 SMs see thousands of independent 64x64 tiles per launch:
+//
+//   build K_zz, K_zx  ->  blocked left-looking Cholesky with the inverse factor built alongside
+//   ->  A = L^-1 K_zx  ->  B = T^T A  ->  column stats + Gauss-Hermite  ->  G_A  ->  dT (+Adam)
+//   ->  dm (+Adam)  ->  G_C = L^-T G_A  ->  G_L  ->  sym(Phi(L^T G_L))  ->  Y  ->  G_K
+//   ->  kernel-parameter / inducing-point gradients  ->  Adam on Z, c, rho_s, rho_l.
+//
+// All O(M^3) products run on the FP64 tensor pipe (mma.sync m8n8k4 f64, "DMMA") from shared
+// memory tiles filled by cp.async double buffering.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TB = 64;            // tile edge; every matrix dimension is padded to a multiple of it
+constexpr int BK = 16;            // k-chunk staged per pipeline stage
+constexpr int LDK = BK + 4;       // smem row stride of a k-contiguous operand tile  [64][LDK]
+constexpr int LDM = TB + 4;       // smem row stride of an m/n-contiguous operand tile [BK][LDM]
+constexpr int STAGE = TB * LDK;   // doubles per operand stage (>= BK*LDM)
+constexpr int GEMM_THREADS = 128;
+constexpr int N_GH = 20;
+constexpr double MIN_VARIANCE = 1e-6;
+constexpr double MEAN_INIT_STD = 1e-3;
+constexpr double BETA1 = 0.9, BETA2 = 0.999, ADAM_EPS = 1e-8;
+
+__constant__ double c_gh_t[N_GH] = {
+    -5.38748089001123276e+00, -4.60368244955074424e+00, -3.94476404011562520e+00, -3.34785456738321630e+00,
+    -2.78880605842813045e+00, -2.25497400208927568e+00, -1.73853771211658614e+00, -1.23407621539532308e+00,
+    -7.37473728545394391e-01, -2.45340708300901239e-01, 2.45340708300901239e-01,  7.37473728545394391e-01,
+    1.23407621539532308e+00,  1.73853771211658614e+00,  2.25497400208927568e+00,  2.78880605842813045e+00,
+    3.34785456738321630e+00,  3.94476404011562520e+00,  4.60368244955074424e+00,  5.38748089001123276e+00};
+__constant__ double c_gh_w[N_GH] = {
+    2.22939364553414471e-13, 4.39934099227317473e-10, 1.08606937076927821e-07, 7.80255647853205987e-06,
+    2.28338636016353646e-04, 3.24377334223785669e-03, 2.48105208874636433e-02, 1.09017206020023294e-01,
+    2.86675505362834149e-01, 4.62243669600610085e-01, 4.62243669600610085e-01, 2.86675505362834149e-01,
+    1.09017206020023294e-01, 2.48105208874636433e-02, 3.24377334223785669e-03, 2.28338636016353646e-04,
+    7.80255647853205987e-06, 1.08606937076927821e-07, 4.39934099227317473e-10, 2.22939364553414471e-13};
+
+// ---------------------------------------------------------------------------------------------
+// region descriptor and workspace layout
+// ---------------------------------------------------------------------------------------------
+struct Region {
+    int M, N;          // training rows (= inducing points), test rows
+    int Mp, Np, Wp;    // padded: Mp = ceil64(M), Np = ceil64(N), Wp = max(Mp, Np)
+    int nb, nbw;       // Mp/64, Wp/64
+    int n_b1;          // first n_b1 training rows carry label -1
+    int train_off, test_off;
+    int orig;          // index in the caller's region order
+    int pad_;
+    long long base;    // offset of the region's buffers in the workspace, in doubles
+};
+
+struct Layout {
+    long long X, Z, Zm, Zv, gZ, Xt, y, m, mm, mv, scal, mu, var, gmu, gv, gsrow, glrow;
+    long long L, Linv, T, Tm, Tv, GA, GC, Kzx, A, Bm, total;
+};
+enum { SC_C = 0, SC_RS = 1, SC_RL = 2, SC_M0 = 3, SC_V0 = 6, SC_N = 16 };
+
+__host__ __device__ inline long long ev2(long long x) { return (x + 1) & ~1LL; }
+
+__host__ __device__ inline Layout make_layout(int Mp, int Np, int Wp, int D) {
+    Layout l;
+    long long o = 0;
+    const long long zd = ev2((long long)Mp * D);
+    l.X = o; o += zd;
+    l.Z = o; o += zd;
+    l.Zm = o; o += zd;
+    l.Zv = o; o += zd;
+    l.gZ = o; o += zd;
+    l.Xt = o; o += ev2((long long)Np * D);
+    l.y = o; o += Mp;
+    l.m = o; o += Mp;
+    l.mm = o; o += Mp;
+    l.mv = o; o += Mp;
+    l.scal = o; o += SC_N;
+    l.mu = o; o += Wp;
+    l.var = o; o += Wp;
+    l.gmu = o; o += Wp;
+    l.gv = o; o += Wp;
+    l.gsrow = o; o += Mp;
+    l.glrow = o; o += Mp;
+    const long long mm = (long long)Mp * Mp, mw = (long long)Mp * Wp;
+    l.L = o; o += mm;
+    l.Linv = o; o += mm;
+    l.T = o; o += mm;
+    l.Tm = o; o += mm;
+    l.Tv = o; o += mm;
+    l.GA = o; o += mm;
+    l.GC = o; o += mm;
+    l.Kzx = o; o += mw;
+    l.A = o; o += mw;
+    l.Bm = o; o += mw;
+    l.total = o;
+    return l;
+}
+
+struct GpParams {
+    int D;
+    double jitter_zz, jitter_xx;
+    double lr_over_bc1, bc2_sqrt;   // Adam scalars of the current step
+    int predict;                    // 1: columns are the test rows
+};
+
+__device__ __forceinline__ double softplus_d(double x) { return log1p(exp(-fabs(x))) + fmax(x, 0.0); }
+__device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+__device__ __forceinline__ void adam_update(double& p, double& m, double& v, double g, const GpParams& prm) {
+    m = BETA1 * m + (1.0 - BETA1) * g;
+    v = BETA2 * v + (1.0 - BETA2) * g * g;
+    p -= prm.lr_over_bc1 * m / (sqrt(v) / prm.bc2_sqrt + ADAM_EPS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 64x64xK tile product on the FP64 tensor pipe
+// ---------------------------------------------------------------------------------------------
+struct GemmSmem {
+    double a[2][STAGE];
+    double b[2][STAGE];
+};
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// Operand tile: 64 rows (m or n) x 16 k.  KC = true: element(r,k) = g[r*ld + k] (k contiguous in
+// global and in smem, [64][LDK]); KC = false: element(r,k) = g[k*ld + r] (r contiguous, [16][LDM]).
+template <bool KC>
+__device__ __forceinline__ void load_stage(double* s, const double* g, int ld, int k) {
+    const int t = threadIdx.x;
+    if (KC) {
+        const int r = t >> 1, h = (t & 1) * 8;
+        const double* src = g + (size_t)r * ld + k + h;
+        double* dst = s + r * LDK + h;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cp_async16(dst + 2 * q, src + 2 * q);
+    } else {
+        const int kr = t >> 3, c = (t & 7) * 8;
+        const double* src = g + (size_t)(k + kr) * ld + c;
+        double* dst = s + kr * LDM + c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cp_async16(dst + 2 * q, src + 2 * q);
+    }
+}
+
+// acc[i][j][e]: row = wm*32 + i*8 + gid, col = wn*32 + j*8 + 2*tig + e
+template <bool AKC, bool BKC>
+__device__ __forceinline__ void gemm_accum(double (&acc)[4][4][2], const double* __restrict__ A, int lda,
+                                           const double* __restrict__ B, int ldb, int k0, int k1,
+                                           const double* __restrict__ kscale, GemmSmem& sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int nchunk = (k1 - k0) / BK;
+    if (nchunk <= 0) return;
+    load_stage<AKC>(sm.a[0], A, lda, k0);
+    load_stage<BKC>(sm.b[0], B, ldb, k0);
+    cp_async_commit();
+    for (int c = 0; c < nchunk; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunk) {
+            load_stage<AKC>(sm.a[buf ^ 1], A, lda, k0 + (c + 1) * BK);
+            load_stage<BKC>(sm.b[buf ^ 1], B, ldb, k0 + (c + 1) * BK);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const double* sa = sm.a[buf];
+        const double* sb = sm.b[buf];
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double af[4], bf[4];
+            const int kq = kk * 4 + tig;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                af[i] = AKC ? sa[(wm * 32 + i * 8 + gid) * LDK + kq] : sa[kq * LDM + wm * 32 + i * 8 + gid];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                bf[j] = BKC ? sb[(wn * 32 + j * 8 + gid) * LDK + kq] : sb[kq * LDM + wn * 32 + j * 8 + gid];
+            if (kscale) {
+                const double sc = kscale[k0 + c * BK + kq];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) af[i] *= sc;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+}
+
+#define ACC_FOREACH(ROW0, COL0, ...)                                          \
+    {                                                                         \
+        const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;         \
+        const int gid_ = lane_ >> 2, tig_ = lane_ & 3;                        \
+        const int wm_ = warp_ >> 1, wn_ = warp_ & 1;                          \
+        _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                    \
+            _Pragma("unroll") for (int j_ = 0; j_ < 4; ++j_) {                \
+                const int row = (ROW0) + wm_ * 32 + i_ * 8 + gid_;            \
+                const int col = (COL0) + wn_ * 32 + j_ * 8 + 2 * tig_;        \
+                double& v0 = acc[i_][j_][0];                                  \
+                double& v1 = acc[i_][j_][1];                                  \
+                __VA_ARGS__                                                   \
+            }                                                                 \
+        }                                                                     \
+    }
+
+enum Phase {
+    PH_BUILD = 0, PH_CHOL, PH_A, PH_B, PH_COLSTATS, PH_GA, PH_GT, PH_GM, PH_GC, PH_GL, PH_SP, PH_Y, PH_GK,
+    PH_KGRAD, PH_ADAM, PH_COUNT
+};
+
+template <int PH>
+__global__ void __launch_bounds__(GEMM_THREADS)
+k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams prm, double* __restrict__ ws) {
+    __shared__ GemmSmem sm;
+    const int4 t = tiles[blockIdx.x];
+    const Region R = regs[t.x];
+    const int ti = t.y, tj = t.z;
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
+    double* base = ws + R.base;
+    const int Mp = R.Mp, Wp = R.Wp;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int r0 = ti * TB, c0 = tj * TB;
+
+    if (PH == PH_A) {          // A = Linv * Kzx, Linv lower: k <= i
+        gemm_accum<true, false>(acc, base + lay.Linv + (size_t)r0 * Mp, Mp, base + lay.Kzx + c0, Wp, 0, r0 + TB,
+                                nullptr, sm);
+        double* out = base + lay.A;
+        ACC_FOREACH(r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
+    } else if (PH == PH_B) {   // B = T^T * A, T lower: k >= i
+        gemm_accum<false, false>(acc, base + lay.T + r0, Mp, base + lay.A + c0, Wp, r0, Mp, nullptr, sm);
+        double* out = base + lay.Bm;
+        ACC_FOREACH(r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
+    } else if (PH == PH_GA) {  // G_A = m g_mu^T + 2 (T B - A) diag(g_v)
+        gemm_accum<true, false>(acc, base + lay.T + (size_t)r0 * Mp, Mp, base + lay.Bm + c0, Wp, 0, r0 + TB, nullptr,
+                                sm);
+        const double* Am = base + lay.A;
+        const double* mv = base + lay.m;
+        const double* gmu = base + lay.gmu;
+        const double* gv = base + lay.gv;
+        double* out = base + lay.GA;
+        ACC_FOREACH(r0, c0, {
+            const double2 a = *reinterpret_cast<const double2*>(Am + (size_t)row * Wp + col);
+            const double mi = mv[row];
+            double2 o;
+            o.x = mi * gmu[col] + 2.0 * gv[col] * (v0 - a.x);
+            o.y = mi * gmu[col + 1] + 2.0 * gv[col + 1] * (v1 - a.y);
+            *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = o;
+        })
+    } else if (PH == PH_GT) {  // dT = tril(2 A diag(g_v) B^T + (T - diag(1/T_ii))/N), Adam on T
+        gemm_accum<true, true>(acc, base + lay.A + (size_t)r0 * Wp, Wp, base + lay.Bm + (size_t)c0 * Wp, Wp, 0, Mp,
+                               base + lay.gv, sm);
+        double* T = base + lay.T;
+        double* Tm = base + lay.Tm;
+        double* Tv = base + lay.Tv;
+        const double invN = 1.0 / (double)R.M;
+        ACC_FOREACH(r0, c0, {
+            _Pragma("unroll") for (int e = 0; e < 2; ++e) {
+                const int cc = col + e;
+                if (row < R.M && cc <= row) {
+                    const size_t idx = (size_t)row * Mp + cc;
+                    double p = T[idx];
+                    double g = 2.0 * (e ? v1 : v0) + (p - (cc == row ? 1.0 / p : 0.0)) * invN;
+                    double m1 = Tm[idx], m2 = Tv[idx];
+                    adam_update(p, m1, m2, g, prm);
+                    T[idx] = p;
+                    Tm[idx] = m1;
+                    Tv[idx] = m2;
+                }
+            }
+        })
+    } else if (PH == PH_GC) {  // G_C = Linv^T * G_A: k >= i
+        gemm_accum<false, false>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, Mp, nullptr, sm);
+        double* out = base + lay.GC;
+        ACC_FOREACH(r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = make_double2(v0, v1); })
+    } else if (PH == PH_GL) {  // G_L = -tril(G_C A^T)   (into the G_A buffer)
+        gemm_accum<true, true>(acc, base + lay.GC + (size_t)r0 * Mp, Mp, base + lay.A + (size_t)c0 * Wp, Wp, 0, Mp,
+                               nullptr, sm);
+        double* out = base + lay.GA;
+        ACC_FOREACH(r0, c0, {
+            double2 o;
+            o.x = (col <= row) ? -v0 : 0.0;
+            o.y = (col + 1 <= row) ? -v1 : 0.0;
+            *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = o;
+        })
+    } else if (PH == PH_SP) {  // symP = 1/2 (P + P^T), P = Phi(L^T G_L): both = 1/2 tril(L^T G_L) mirrored
+        gemm_accum<false, false>(acc, base + lay.L + r0, Mp, base + lay.GA + c0, Mp, r0, Mp, nullptr, sm);
+        double* out = base + lay.Bm;
+        ACC_FOREACH(r0, c0, {
+            _Pragma("unroll") for (int e = 0; e < 2; ++e) {
+                const int cc = col + e;
+                const double v = 0.5 * (e ? v1 : v0);
+                if (cc <= row) {
+                    out[(size_t)row * Wp + cc] = v;
+                    if (cc < row) out[(size_t)cc * Wp + row] = v;
+                }
+            }
+        })
+    } else if (PH == PH_Y) {   // Y = symP * Linv: k >= j   (into the G_A buffer)
+        gemm_accum<true, false>(acc, base + lay.Bm + (size_t)r0 * Wp, Wp, base + lay.Linv + c0, Mp, c0, Mp, nullptr,
+                                sm);
+        double* out = base + lay.GA;
+        ACC_FOREACH(r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = make_double2(v0, v1); })
+    } else if (PH == PH_GK) {  // G_K = Linv^T * Y: k >= i   (into the B buffer)
+        gemm_accum<false, false>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, Mp, nullptr, sm);
+        double* out = base + lay.Bm;
+        ACC_FOREACH(r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel matrices: K_zz = s exp(-r2/2) + jitter I (lower tiles), K_zx = s exp(-r2/2)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_build(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams prm, double* __restrict__ ws) {
+    extern __shared__ double smem_build[];
+    const int D = prm.D;
+    const int4 t = tiles[blockIdx.x];
+    const Region R = regs[t.x];
+    const int ti = t.y, tj = t.z;
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
+    double* base = ws + R.base;
+    double* zi = smem_build;
+    double* zj = zi + TB * D;
+    double* xj = zj + TB * D;
+    const double* Z = base + lay.Z;
+    const double* Xc = prm.predict ? base + lay.Xt : base + lay.X;
+    const int ncols = prm.predict ? R.N : R.M;       // valid columns of K_zx
+    const int colrows = prm.predict ? R.Np : R.Mp;   // allocated rows of the column matrix
+    const bool do_zz = (tj <= ti) && (tj < R.nb);
+    for (int e = threadIdx.x; e < TB * D; e += blockDim.x) {
+        zi[e] = Z[(size_t)ti * TB * D + e];
+        zj[e] = do_zz ? Z[(size_t)tj * TB * D + e] : 0.0;
+        xj[e] = ((tj + 1) * TB <= colrows) ? Xc[(size_t)tj * TB * D + e] : 0.0;
+    }
+    __syncthreads();
+    const double* sc = base + lay.scal;
+    const double ell = softplus_d(sc[SC_RL]), s = softplus_d(sc[SC_RS]);
+    const double inv_l2 = 1.0 / (ell * ell);
+    double* Kzx = base + lay.Kzx;
+    double* Kzz = base + lay.L;
+    for (int e = threadIdx.x; e < TB * TB; e += blockDim.x) {
+        const int li = e >> 6, lj = e & 63;
+        const int i = ti * TB + li, j = tj * TB + lj;
+        double d2 = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const double df = zi[li * D + d] - xj[lj * D + d];
+            d2 += df * df;
+        }
+        Kzx[(size_t)i * R.Wp + j] = (i < R.M && j < ncols) ? s * exp(-0.5 * (d2 * inv_l2)) : 0.0;
+        if (do_zz) {
+            double q2 = 0.0;
+            for (int d = 0; d < D; ++d) {
+                const double df = zi[li * D + d] - zj[lj * D + d];
+                q2 += df * df;
+            }
+            double v;
+            if (i < R.M && j < R.M)
+                v = s * exp(-0.5 * (q2 * inv_l2)) + (i == j ? prm.jitter_zz : 0.0);
+            else
+                v = (i == j) ? 1.0 : 0.0;
+            Kzz[(size_t)i * R.Mp + j] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// blocked left-looking Cholesky with the inverse factor, block step kb
+//   diag : C = K[kb,kb] - sum_{j<kb} L[kb,j] L[kb,j]^T ; L_kk = chol(C) ; Linv_kk = L_kk^-1
+//   panel: L[i,kb] = (K[i,kb] - sum_{j<kb} L[i,j] L[kb,j]^T) Linv_kk^T          (i > kb)
+//          Linv[kb,j] = -Linv_kk sum_{k=j..kb-1} L[kb,k] Linv[k,j]              (j < kb)
+// ---------------------------------------------------------------------------------------------
+constexpr int LDS_ = TB + 1;
+constexpr int DIAG_SMEM = (int)sizeof(GemmSmem) + TB * LDS_ * (int)sizeof(double);
+static_assert(TB * LDS_ * sizeof(double) <= sizeof(GemmSmem), "inverse tile must fit in the GEMM stages");
+
+__global__ void __launch_bounds__(GEMM_THREADS)
+k_chol_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __restrict__ ws, int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_diag[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_diag);
+    double* sL = reinterpret_cast<double*>(smem_diag + sizeof(GemmSmem));
+    double* sX = reinterpret_cast<double*>(smem_diag);   // aliases the GEMM stages (dead after the product)
+    const Region R = regs[blockIdx.x];
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
+    double* base = ws + R.base;
+    const int Mp = R.Mp;
+    double* Lg = base + lay.L;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int r0 = kb * TB;
+    gemm_accum<true, true>(acc, Lg + (size_t)r0 * Mp, Mp, Lg + (size_t)r0 * Mp, Mp, 0, r0, nullptr, sm);
+    ACC_FOREACH(0, 0, {
+        const double2 k = *reinterpret_cast<const double2*>(Lg + (size_t)(r0 + row) * Mp + r0 + col);
+        sL[row * LDS_ + col] = k.x - v0;
+        sL[row * LDS_ + col + 1] = k.y - v1;
+    })
+    __syncthreads();
+    // unblocked right-looking Cholesky of the 64x64 tile (lower)
+    const int tid = threadIdx.x;
+    const int rr = tid & 63, half = tid >> 6;
+    bool bad = false;
+    for (int c = 0; c < TB; ++c) {
+        double d = sL[c * LDS_ + c];
+        if (!(d > 0.0)) {
+            bad = true;
+            d = 1.0;
+        }
+        const double piv = sqrt(d);
+        double l = 0.0;
+        if (half == 0 && rr > c) l = sL[rr * LDS_ + c] / piv;
+        __syncthreads();
+        if (half == 0) {
+            if (rr > c) sL[rr * LDS_ + c] = l;
+            if (rr == c) sL[c * LDS_ + c] = piv;
+        }
+        __syncthreads();
+        if (rr > c) {
+            const double lr = sL[rr * LDS_ + c];
+            for (int cc = c + 1 + half; cc <= rr; cc += 2) sL[rr * LDS_ + cc] -= lr * sL[cc * LDS_ + c];
+        }
+        __syncthreads();
+    }
+    if (bad && tid == 0) atomicOr(status + R.orig, GAPRO_GP_NOT_PSD);
+    // inverse of the lower-triangular tile, one column per thread
+    if (tid < TB) {
+        const int c = tid;
+        sX[c * LDS_ + c] = 1.0 / sL[c * LDS_ + c];
+        for (int r = c + 1; r < TB; ++r) {
+            double s = 0.0;
+            for (int k = c; k < r; ++k) s += sL[r * LDS_ + k] * sX[k * LDS_ + c];
+            sX[r * LDS_ + c] = -s / sL[r * LDS_ + r];
+        }
+    }
+    __syncthreads();
+    double* Li = base + lay.Linv;
+    for (int e = tid; e < TB * TB; e += GEMM_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        const bool low = c <= r;
+        Lg[(size_t)(r0 + r) * Mp + r0 + c] = low ? sL[r * LDS_ + c] : 0.0;
+        Li[(size_t)(r0 + r) * Mp + r0 + c] = low ? sX[r * LDS_ + c] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS)
+k_chol_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, int kb, GpParams prm,
+             double* __restrict__ ws, double* __restrict__ scratch) {
+    __shared__ GemmSmem sm;
+    const int2 pt = ptiles[blockIdx.x];
+    const Region R = regs[pt.x];
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
+    double* base = ws + R.base;
+    const int Mp = R.Mp;
+    double* Lg = base + lay.L;
+    double* Li = base + lay.Linv;
+    double* tmp = scratch + (size_t)blockIdx.x * TB * TB;   // this CTA's 64x64 intermediate
+    const int r0 = kb * TB;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    if (pt.y >= kb) {
+        // L panel tile i = pt.y + 1 > kb
+        const int i0 = (pt.y + 1) * TB;
+        gemm_accum<true, true>(acc, Lg + (size_t)i0 * Mp, Mp, Lg + (size_t)r0 * Mp, Mp, 0, r0, nullptr, sm);
+        ACC_FOREACH(0, 0, {
+            const double2 k = *reinterpret_cast<const double2*>(Lg + (size_t)(i0 + row) * Mp + r0 + col);
+            *reinterpret_cast<double2*>(tmp + row * TB + col) = make_double2(k.x - v0, k.y - v1);
+        })
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        // out[r,c] = sum_k tmp[r,k] Linv_kk[c,k]
+        gemm_accum<true, true>(acc, tmp, TB, Li + (size_t)r0 * Mp + r0, Mp, 0, TB, nullptr, sm);
+        ACC_FOREACH(0, 0, {
+            *reinterpret_cast<double2*>(Lg + (size_t)(i0 + row) * Mp + r0 + col) = make_double2(v0, v1);
+        })
+    } else {
+        // Linv row tile j = pt.y < kb
+        const int j0 = pt.y * TB;
+        gemm_accum<true, false>(acc, Lg + (size_t)r0 * Mp, Mp, Li + j0, Mp, j0, r0, nullptr, sm);
+        ACC_FOREACH(0, 0, { *reinterpret_cast<double2*>(tmp + row * TB + col) = make_double2(v0, v1); })
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        // out[r,c] = -sum_k Linv_kk[r,k] tmp[k,c]
+        gemm_accum<true, false>(acc, Li + (size_t)r0 * Mp + r0, Mp, tmp, TB, 0, TB, nullptr, sm);
+        ACC_FOREACH(0, 0, {
+            *reinterpret_cast<double2*>(Li + (size_t)(r0 + row) * Mp + j0 + col) = make_double2(-v0, -v1);
+        })
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// column statistics: mu = A^T m + c, var = s + jitter_xx + colsum(B^2) - colsum(A^2), then either
+// the Gauss-Hermite gradients g_mu, g_v (training) or the outputs (prediction)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double hazard(double z) {
+    // phi(z)/Phi(z) = sqrt(2/pi) / erfcx(-z/sqrt2)
+    return 0.79788456080286535588 / erfcx(-z * 0.70710678118654752440);
+}
+
+struct PredictOut {
+    float *prob, *conf, *mu, *var;
+    uint8_t* label;
+    double *mu64, *var64;
+    int32_t* status;
+};
+
+__global__ void __launch_bounds__(256)
+k_colstats(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpParams prm, double* __restrict__ ws,
+           PredictOut po) {
+    __shared__ double red[3][4][TB];
+    const int2 rt = rtiles[blockIdx.x];
+    const Region R = regs[rt.x];
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
+    double* base = ws + R.base;
+    const int Wp = R.Wp;
+    const int cl = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int n = rt.y * TB + cl;
+    const double* A = base + lay.A;
+    const double* Bm = base + lay.Bm;
+    const double* mv = base + lay.m;
+    double s_mu = 0.0, s_b = 0.0, s_a = 0.0;
+    for (int k = q; k < R.Mp; k += 4) {
+        const double a = A[(size_t)k * Wp + n], b = Bm[(size_t)k * Wp + n];
+        s_mu += a * mv[k];
+        s_b += b * b;
+        s_a += a * a;
+    }
+    red[0][q][cl] = s_mu;
+    red[1][q][cl] = s_b;
+    red[2][q][cl] = s_a;
+    __syncthreads();
+    if (q != 0) return;
+    s_mu = ((red[0][0][cl] + red[0][1][cl]) + red[0][2][cl]) + red[0][3][cl];
+    s_b = ((red[1][0][cl] + red[1][1][cl]) + red[1][2][cl]) + red[1][3][cl];
+    s_a = ((red[2][0][cl] + red[2][1][cl]) + red[2][2][cl]) + red[2][3][cl];
+    const double* sc = base + lay.scal;
+    const double s = softplus_d(sc[SC_RS]);
+    const double mu = s_mu + sc[SC_C];
+    const double v = s + prm.jitter_xx + s_b - s_a;
+    const bool clamped = v < MIN_VARIANCE;
+    const double var = clamped ? MIN_VARIANCE : v;
+    if (prm.predict) {
+        if (n < R.N) {
+            const double link = mu / sqrt(1.0 + var);
+            const double p = 0.5 * erfc(-link * 0.70710678118654752440);
+            const float pf = (float)p;
+            const bool lab = pf >= 0.5f;
+            const int o = R.test_off + n;
+            po.prob[o] = pf;
+            po.label[o] = lab ? 1 : 0;
+            po.conf[o] = lab ? pf : (1.0f - pf);
+            po.mu[o] = (float)mu;
+            po.var[o] = (float)var;
+            if (po.mu64) po.mu64[o] = mu;
+            if (po.var64) po.var64[o] = var;
+            if (!(isfinite(mu) && isfinite(var))) atomicOr(po.status + R.orig, GAPRO_GP_NAN);
+        }
+        return;
+    }
+    double gmu = 0.0, gv = 0.0;
+    if (n < R.M) {
+        const double y = base[lay.y + n];
+        const double sd = sqrt(2.0 * var);
+        double a0 = 0.0, a1 = 0.0;
+        for (int k = 0; k < N_GH; ++k) {
+            const double h = hazard(y * (sd * c_gh_t[k] + mu));
+            a0 += c_gh_w[k] * h;
+            a1 += c_gh_w[k] * c_gh_t[k] * h;
+        }
+        const double pref = -(1.0 / (double)R.M) * 0.56418958354775628695;   // -(1/N)/sqrt(pi)
+        gmu = pref * y * a0;
+        gv = clamped ? 0.0 : pref * y * a1 / sd;
+    }
+    base[lay.mu + n] = mu;
+    base[lay.var + n] = var;
+    base[lay.gmu + n] = gmu;
+    base[lay.gv + n] = gv;
+}
+
+// dm = A g_mu + m/N, Adam on m.  One warp per row.
+__global__ void __launch_bounds__(256)
+k_grad_m(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpParams prm, double* __restrict__ ws) {
+    const int2 rt = rtiles[blockIdx.x];
+    const Region R = regs[rt.x];
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
+    double* base = ws + R.base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* gmu = base + lay.gmu;
+    for (int rr = 0; rr < 8; ++rr) {
+        const int i = rt.y * TB + warp * 8 + rr;
+        if (i >= R.M) break;
+        const double* Arow = base + lay.A + (size_t)i * R.Wp;
+        double s = 0.0;
+        for (int n = lane; n < R.M; n += 32) s += Arow[n] * gmu[n];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            double p = base[lay.m + i], m1 = base[lay.mm + i], m2 = base[lay.mv + i];
+            const double g = s + p / (double)R.M;
+            adam_update(p, m1, m2, g, prm);
+            base[lay.m + i] = p;
+            base[lay.mm + i] = m1;
+            base[lay.mv + i] = m2;
+        }
+    }
+}
+
+// Gradients w.r.t. the inducing points and the raw kernel parameters from G_K (in the B buffer,
+// symmetric) and G_C.  One warp per inducing row.
+template <int DMAX>
+__global__ void __launch_bounds__(256)
+k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpParams prm, double* __restrict__ ws) {
+    const int2 rt = rtiles[blockIdx.x];
+    const Region R = regs[rt.x];
+    const int D = prm.D;
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
+    double* base = ws + R.base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* sc = base + lay.scal;
+    const double ell = softplus_d(sc[SC_RL]), s = softplus_d(sc[SC_RS]);
+    const double inv_l2 = 1.0 / (ell * ell);
+    const double* Z = base + lay.Z;
+    const double* X = base + lay.X;
+    for (int rr = 0; rr < 8; ++rr) {
+        const int i = rt.y * TB + warp * 8 + rr;
+        if (i >= R.M) break;
+        double zi[DMAX], az[DMAX];
+#pragma unroll
+        for (int d = 0; d < DMAX; ++d) {
+            zi[d] = d < D ? Z[(size_t)i * D + d] : 0.0;
+            az[d] = 0.0;
+        }
+        double as = 0.0, al = 0.0;
+        const double* GK = base + lay.Bm + (size_t)i * R.Wp;
+        const double* GC = base + lay.GC + (size_t)i * R.Mp;
+        const double* Kx = base + lay.Kzx + (size_t)i * R.Wp;
+        for (int j = lane; j < R.M; j += 32) {
+            // zz part: W = Gr + Gr^T = 2 Gr (G_K and K_zz symmetric)
+            const double* zj = Z + (size_t)j * D;
+            double d2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d) {
+                const double df = d < D ? zi[d] - zj[d] : 0.0;
+                d2 += df * df;
+            }
+            double r2 = d2 * inv_l2;
+            const double E = exp(-0.5 * r2);
+            double G = GK[j];
+            double Gr = -0.5 * G * (s * E);
+            as += G * E;
+            al += Gr * (-2.0 * r2 / ell);
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d)
+                if (d < D) az[d] += 2.0 * Gr * (zi[d] - zj[d]);
+            // zx part
+            const double* xj = X + (size_t)j * D;
+            d2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d) {
+                const double df = d < D ? zi[d] - xj[d] : 0.0;
+                d2 += df * df;
+            }
+            r2 = d2 * inv_l2;
+            const double Kv = Kx[j];
+            G = GC[j];
+            Gr = -0.5 * G * Kv;
+            as += G * (Kv / s);
+            al += Gr * (-2.0 * r2 / ell);
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d)
+                if (d < D) az[d] += Gr * (zi[d] - xj[d]);
+        }
+        for (int o = 16; o; o >>= 1) {
+            as += __shfl_xor_sync(0xffffffffu, as, o);
+            al += __shfl_xor_sync(0xffffffffu, al, o);
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d) az[d] += __shfl_xor_sync(0xffffffffu, az[d], o);
+        }
+        if (lane == 0) {
+            base[lay.gsrow + i] = as;
+            base[lay.glrow + i] = al;
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d)
+                if (d < D) base[lay.gZ + (size_t)i * D + d] = 2.0 * inv_l2 * az[d];
+        }
+    }
+}
+
+// Adam on Z and on the three scalars (c, rho_s, rho_l).  One CTA per region.
+__device__ double block_sum(double v, double* red) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    red[tid] = v;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (tid < s) red[tid] += red[tid + s];
+        __syncthreads();
+    }
+    return red[0];
+}
+
+__global__ void __launch_bounds__(256)
+k_adam_small(const Region* __restrict__ regs, GpParams prm, double* __restrict__ ws) {
+    __shared__ double red[256];
+    const Region R = regs[blockIdx.x];
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
+    double* base = ws + R.base;
+    const int tid = threadIdx.x;
+    const int MD = R.M * prm.D;
+    for (int e = tid; e < MD; e += blockDim.x) {
+        double p = base[lay.Z + e], m1 = base[lay.Zm + e], m2 = base[lay.Zv + e];
+        adam_update(p, m1, m2, base[lay.gZ + e], prm);
+        base[lay.Z + e] = p;
+        base[lay.Zm + e] = m1;
+        base[lay.Zv + e] = m2;
+    }
+    double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
+    for (int i = tid; i < R.M; i += blockDim.x) {
+        a += base[lay.gmu + i];
+        b += base[lay.gv + i];
+        c += base[lay.gsrow + i];
+        d += base[lay.glrow + i];
+    }
+    const double g_c = block_sum(a, red);
+    const double g_v = block_sum(b, red);
+    const double g_sr = block_sum(c, red);
+    const double g_lr = block_sum(d, red);
+    if (tid == 0) {
+        double* sc = base + lay.scal;
+        const double g[3] = {g_c, (g_v + g_sr) * sigmoid_d(sc[SC_RS]), g_lr * sigmoid_d(sc[SC_RL])};
+        for (int k = 0; k < 3; ++k) {
+            double p = sc[k], m1 = sc[SC_M0 + k], m2 = sc[SC_V0 + k];
+            adam_update(p, m1, m2, g[k], prm);
+            sc[k] = p;
+            sc[SC_M0 + k] = m1;
+            sc[SC_V0 + k] = m2;
+        }
+    }
+}
+
+// initial state: X, Z <- training rows (float32 widened), Xt <- test rows, y, m <- 1e-3 * noise, T <- I
+__global__ void __launch_bounds__(256)
+k_region_init(const Region* __restrict__ regs, int D, const float* __restrict__ feats, const int32_t* __restrict__ train_idx,
+              const int32_t* __restrict__ test_idx, const float* __restrict__ noise, double* __restrict__ ws) {
+    const Region R = regs[blockIdx.x];
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
+    double* base = ws + R.base;
+    for (int e = threadIdx.x; e < R.M * D; e += blockDim.x) {
+        const int i = e / D, d = e % D;
+        const double v = (double)feats[(size_t)train_idx[R.train_off + i] * D + d];
+        base[lay.X + e] = v;
+        base[lay.Z + e] = v;
+    }
+    for (int e = threadIdx.x; e < R.N * D; e += blockDim.x) {
+        const int i = e / D, d = e % D;
+        base[lay.Xt + e] = (double)feats[(size_t)test_idx[R.test_off + i] * D + d];
+    }
+    for (int i = threadIdx.x; i < R.Mp; i += blockDim.x) {
+        base[lay.T + (size_t)i * R.Mp + i] = 1.0;
+        if (i < R.M) {
+            base[lay.y + i] = i < R.n_b1 ? -1.0 : 1.0;
+            base[lay.m + i] = MEAN_INIT_STD * (double)noise[R.train_off + i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+inline int ceil64(int x) { return (x + 63) / 64 * 64; }
+
+Region make_region(int M, int N, int n_b1, int train_off, int test_off, int orig) {
+    Region r;
+    r.M = M;
+    r.N = N;
+    r.Mp = ceil64(M);
+    r.Np = ceil64(N);
+    r.Wp = std::max(r.Mp, r.Np);
+    r.nb = r.Mp / TB;
+    r.nbw = r.Wp / TB;
+    r.n_b1 = n_b1;
+    r.train_off = train_off;
+    r.test_off = test_off;
+    r.orig = orig;
+    r.pad_ = 0;
+    r.base = 0;
+    return r;
+}
+
+size_t region_doubles(const Region& r, int D) {
+    return (size_t)gapro_align_up((size_t)make_layout(r.Mp, r.Np, r.Wp, D).total, 32);
+}
+
+// bytes of tables + descriptors + panel scratch for a set of regions
+size_t aux_bytes(const std::vector<Region>& rs) {
+    size_t full = 0, lower = 0, wide = 0, rows = 0, rowsp = 0, panel = 0;
+    for (const Region& r : rs) {
+        full += (size_t)r.nb * r.nb;
+        lower += (size_t)r.nb * (r.nb + 1) / 2;
+        wide += (size_t)r.nb * r.nbw;
+        rows += r.nb;
+        rowsp += r.Np / TB;
+        panel += r.nb - 1;
+    }
+    size_t b = 0;
+    b += gapro_align_up(rs.size() * sizeof(Region), 256);
+    b += gapro_align_up(full * 16, 256) + gapro_align_up(lower * 16, 256) + gapro_align_up(wide * 16, 256);
+    b += gapro_align_up(rows * 8, 256) + gapro_align_up(rowsp * 8, 256) + gapro_align_up(panel * 8, 256);
+    b += gapro_align_up(panel * TB * TB * 8, 256);
+    return b + 256;
+}
+
+thread_local int64_t g_launches = 0;
+
+struct ChunkTables {
+    Region* regs;
+    int4 *full, *lower, *wide;
+    int2 *rows, *rowsp, *panel;
+    double* scratch;
+    int n_full, n_lower, n_wide, n_rows, n_rowsp;
+    std::vector<int> cnt_gt;        // cnt_gt[kb] = #regions with nb > kb
+    std::vector<int> panel_prefix;  // panel tiles of the first cnt_gt[kb] regions
+    int nbmax;
+};
+
+struct Driver {
+    cudaStream_t stream;
+    int D;
+    double lr, jitter_zz, jitter_xx;
+    double* ws;
+    int n_regs;
+    ChunkTables tb;
+    PredictOut po;
+
+    GpParams params(int step, int predict) const {
+        GpParams p;
+        p.D = D;
+        p.jitter_zz = jitter_zz;
+        p.jitter_xx = jitter_xx;
+        p.predict = predict;
+        if (step > 0) {
+            p.lr_over_bc1 = lr / (1.0 - pow(BETA1, (double)step));
+            p.bc2_sqrt = sqrt(1.0 - pow(BETA2, (double)step));
+        } else {
+            p.lr_over_bc1 = 0.0;
+            p.bc2_sqrt = 1.0;
+        }
+        return p;
+    }
+
+    template <int PH>
+    void gemm(const int4* tiles, int n, const GpParams& p) {
+        if (n <= 0) return;
+        k_gemm<PH><<<n, GEMM_THREADS, 0, stream>>>(tb.regs, tiles, p, ws);
+        ++g_launches;
+    }
+
+    void build(const GpParams& p) {
+        const int4* tiles = p.predict ? tb.wide : tb.full;
+        const int n = p.predict ? tb.n_wide : tb.n_full;
+        k_build<<<n, 256, 3 * TB * D * sizeof(double), stream>>>(tb.regs, tiles, p, ws);
+        ++g_launches;
+    }
+
+    void cholesky(const GpParams& p) {
+        for (int kb = 0; kb < tb.nbmax; ++kb) {
+            const int live = tb.cnt_gt[kb];
+            if (live <= 0) break;
+            k_chol_diag<<<live, GEMM_THREADS, DIAG_SMEM, stream>>>(tb.regs, kb, p, ws, po.status);
+            ++g_launches;
+            const int np = tb.panel_prefix[kb];
+            if (np > 0) {
+                k_chol_panel<<<np, GEMM_THREADS, 0, stream>>>(tb.regs, tb.panel, kb, p, ws, tb.scratch);
+                ++g_launches;
+            }
+        }
+    }
+
+    void kgrad(const GpParams& p) {
+        if (D <= 8)
+            k_kgrad<8><<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+        else if (D <= 32)
+            k_kgrad<32><<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+        else
+            k_kgrad<64><<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+        ++g_launches;
+    }
+
+    // one training step; stop_phase < PH_COUNT truncates it (debug)
+    void train_step(int step, int stop_phase) {
+        const GpParams p = params(step, 0);
+        int ph = 0;
+#define PHASE(X)                     \
+    if (ph++ >= stop_phase) return;  \
+    X;
+        PHASE(build(p))
+        PHASE(cholesky(p))
+        PHASE(gemm<PH_A>(tb.full, tb.n_full, p))
+        PHASE(gemm<PH_B>(tb.full, tb.n_full, p))
+        PHASE((k_colstats<<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws, po), ++g_launches))
+        PHASE(gemm<PH_GA>(tb.full, tb.n_full, p))
+        PHASE(gemm<PH_GT>(tb.lower, tb.n_lower, p))
+        PHASE((k_grad_m<<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws), ++g_launches))
+        PHASE(gemm<PH_GC>(tb.full, tb.n_full, p))
+        PHASE(gemm<PH_GL>(tb.lower, tb.n_lower, p))
+        PHASE(gemm<PH_SP>(tb.lower, tb.n_lower, p))
+        PHASE(gemm<PH_Y>(tb.full, tb.n_full, p))
+        PHASE(gemm<PH_GK>(tb.full, tb.n_full, p))
+        PHASE(kgrad(p))
+        PHASE((k_adam_small<<<n_regs, 256, 0, stream>>>(tb.regs, p, ws), ++g_launches))
+#undef PHASE
+    }
+
+    void predict() {
+        const GpParams p = params(0, 1);
+        build(p);
+        cholesky(p);
+        gemm<PH_A>(tb.wide, tb.n_wide, p);
+        gemm<PH_B>(tb.wide, tb.n_wide, p);
+        if (tb.n_rowsp > 0) {
+            k_colstats<<<tb.n_rowsp, 256, 0, stream>>>(tb.regs, tb.rowsp, p, ws, po);
+            ++g_launches;
+        }
+    }
+};
+
+// lays out one chunk (regions already carry .base), uploads descriptors and tile tables
+int setup_chunk(std::vector<Region>& rs, char* aux, cudaStream_t stream, ChunkTables& tb) {
+    std::vector<int4> full, lower, wide;
+    std::vector<int2> rows, rowsp, panel;
+    tb.nbmax = 0;
+    for (size_t r = 0; r < rs.size(); ++r) tb.nbmax = std::max(tb.nbmax, rs[r].nb);
+    tb.cnt_gt.assign(tb.nbmax + 1, 0);
+    tb.panel_prefix.assign(tb.nbmax + 1, 0);
+    std::vector<int> panel_before(rs.size() + 1, 0);
+    for (size_t r = 0; r < rs.size(); ++r) {
+        const Region& R = rs[r];
+        for (int ti = 0; ti < R.nb; ++ti) {
+            for (int tj = 0; tj < R.nb; ++tj) full.push_back(make_int4((int)r, ti, tj, 0));
+            for (int tj = 0; tj <= ti; ++tj) lower.push_back(make_int4((int)r, ti, tj, 0));
+            for (int tj = 0; tj < R.nbw; ++tj) wide.push_back(make_int4((int)r, ti, tj, 0));
+            rows.push_back(make_int2((int)r, ti));
+        }
+        for (int t = 0; t < R.Np / TB; ++t)
+            if (t * TB < R.N) rowsp.push_back(make_int2((int)r, t));
+        for (int t = 0; t < R.nb - 1; ++t) panel.push_back(make_int2((int)r, t));
+        panel_before[r + 1] = (int)panel.size();
+        for (int kb = 0; kb < R.nb; ++kb) tb.cnt_gt[kb]++;
+    }
+    // regions are sorted by nb descending, so {nb > kb} is the prefix of length cnt_gt[kb]
+    for (int kb = 0; kb <= tb.nbmax; ++kb) tb.panel_prefix[kb] = panel_before[tb.cnt_gt[kb]];
+    size_t o = 0;
+    auto put = [&](const void* src, size_t bytes) -> char* {
+        char* dst = aux + o;
+        o += gapro_align_up(bytes ? bytes : 1, 256);
+        if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+        return dst;
+    };
+    tb.regs = (Region*)put(rs.data(), rs.size() * sizeof(Region));
+    tb.full = (int4*)put(full.data(), full.size() * 16);
+    tb.lower = (int4*)put(lower.data(), lower.size() * 16);
+    tb.wide = (int4*)put(wide.data(), wide.size() * 16);
+    tb.rows = (int2*)put(rows.data(), rows.size() * 8);
+    tb.rowsp = (int2*)put(rowsp.data(), rowsp.size() * 8);
+    tb.panel = (int2*)put(panel.data(), panel.size() * 8);
+    tb.scratch = (double*)(aux + o);
+    tb.n_full = (int)full.size();
+    tb.n_lower = (int)lower.size();
+    tb.n_wide = (int)wide.size();
+    tb.n_rows = (int)rows.size();
+    tb.n_rowsp = (int)rowsp.size();
+    // the host vectors die at return: the copies above must have been consumed
+    GAPRO_CUDA_TRY(cudaStreamSynchronize(stream));
+    return GAPRO_OK;
+}
+
+int check_device() {
+    int dev = 0;
+    GAPRO_CUDA_TRY(cudaGetDevice(&dev));
+    return GAPRO_OK;
+}
+
+std::vector<Region> sorted_regions(int n_regions, const int32_t* train_off, const int32_t* n_b1,
+                                   const int32_t* test_off) {
+    std::vector<Region> rs;
+    rs.reserve(n_regions);
+    for (int r = 0; r < n_regions; ++r)
+        rs.push_back(make_region(train_off[r + 1] - train_off[r], test_off[r + 1] - test_off[r], n_b1 ? n_b1[r] : 0,
+                                 train_off[r], test_off[r], r));
+    std::stable_sort(rs.begin(), rs.end(), [](const Region& a, const Region& b) {
+        if (a.nb != b.nb) return a.nb > b.nb;
+        return a.nbw > b.nbw;
+    });
+    return rs;
+}
+
+}  // namespace
+
+extern "C" size_t gapro_gp_workspace_bytes(int32_t n_regions, const int32_t* train_off, const int32_t* test_off,
+                                           int32_t D) {
+    if (n_regions <= 0 || !train_off || !test_off || D <= 0) return 0;
+    std::vector<Region> rs = sorted_regions(n_regions, train_off, nullptr, test_off);
+    size_t doubles = 0;
+    for (const Region& r : rs) doubles += region_doubles(r, D);
+    return doubles * 8 + aux_bytes(rs);
+}
+
+extern "C" size_t gapro_gp_min_workspace_bytes(int32_t n_regions, const int32_t* train_off, const int32_t* test_off,
+                                               int32_t D) {
+    if (n_regions <= 0 || !train_off || !test_off || D <= 0) return 0;
+    std::vector<Region> rs = sorted_regions(n_regions, train_off, nullptr, test_off);
+    size_t best = 0;
+    for (const Region& r : rs) {
+        std::vector<Region> one(1, r);
+        best = std::max(best, region_doubles(r, D) * 8 + aux_bytes(one));
+    }
+    return best;
+}
+
+extern "C" int64_t gapro_gp_last_launch_count(void) { return g_launches; }
+
+static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& all, const int32_t* train_idx,
+                       const int32_t* test_idx, const float* init_noise, int32_t iters, int32_t stop_phase, double lr,
+                       double jitter_zz, double jitter_xx, PredictOut po, void* ws, size_t ws_bytes, bool do_predict,
+                       cudaStream_t stream) {
+    GAPRO_REQUIRE(D >= 1 && D <= 64, "gp: feature dimension %d not in [1, 64]", D);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TB * 64 * 8));
+        GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+        attr_set = true;
+    }
+    size_t pos = 0;
+    while (pos < all.size()) {
+        // greedy chunk: as many regions (already sorted by size) as fit in the workspace
+        std::vector<Region> chunk;
+        size_t doubles = 0;
+        while (pos + chunk.size() < all.size()) {
+            Region r = all[pos + chunk.size()];
+            r.base = (long long)doubles;
+            chunk.push_back(r);
+            size_t nd = doubles + region_doubles(r, D);
+            if (nd * 8 + aux_bytes(chunk) > ws_bytes) {
+                chunk.pop_back();
+                break;
+            }
+            doubles = nd;
+        }
+        if (chunk.empty()) {
+            gapro_set_error("gapro_gp_fit_batch: workspace of %zu bytes cannot hold a region with M=%d N=%d", ws_bytes,
+                            all[pos].M, all[pos].N);
+            return GAPRO_ERR_WORKSPACE;
+        }
+        Driver drv;
+        drv.stream = stream;
+        drv.D = D;
+        drv.lr = lr;
+        drv.jitter_zz = jitter_zz;
+        drv.jitter_xx = jitter_xx;
+        drv.ws = (double*)ws;
+        drv.n_regs = (int)chunk.size();
+        drv.po = po;
+        GAPRO_CUDA_TRY(cudaMemsetAsync(ws, 0, doubles * 8, stream));
+        int rc = setup_chunk(chunk, (char*)ws + doubles * 8, stream, drv.tb);
+        if (rc != GAPRO_OK) return rc;
+        k_region_init<<<drv.n_regs, 256, 0, stream>>>(drv.tb.regs, D, feats_spp, train_idx, test_idx, init_noise,
+                                                      drv.ws);
+        ++g_launches;
+        for (int it = 1; it <= iters; ++it) drv.train_step(it, PH_COUNT);
+        if (stop_phase > 0) drv.train_step(iters + 1, stop_phase);
+        if (do_predict) drv.predict();
+        GAPRO_KERNEL_CHECK();
+        pos += chunk.size();
+        if (pos < all.size()) GAPRO_CUDA_TRY(cudaStreamSynchronize(stream));   // workspace is reused
+    }
+    return GAPRO_OK;
+}
+
+extern "C" int gapro_gp_fit_batch(const float* feats_spp, int32_t D, int32_t n_regions, const int32_t* train_off,
+                                  const int32_t* n_b1, const int32_t* test_off, const int32_t* train_idx,
+                                  const int32_t* test_idx, const float* init_noise, int32_t iters, double lr,
+                                  double jitter_zz, double jitter_xx, float* out_prob, float* out_conf,
+                                  uint8_t* out_label, float* out_mu, float* out_var, double* out_mu64,
+                                  double* out_var64, int32_t* status, void* ws, size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    g_launches = 0;
+    if (n_regions == 0) return GAPRO_OK;
+    GAPRO_REQUIRE(n_regions > 0 && feats_spp && train_off && n_b1 && test_off && train_idx && test_idx && init_noise &&
+                      out_prob && out_conf && out_label && out_mu && out_var && status && ws,
+                  "gapro_gp_fit_batch: null pointer");
+    GAPRO_REQUIRE(iters >= 0, "gapro_gp_fit_batch: iters < 0");
+    for (int r = 0; r < n_regions; ++r) {
+        const int M = train_off[r + 1] - train_off[r], N = test_off[r + 1] - test_off[r];
+        GAPRO_REQUIRE(M >= 1 && N >= 1 && n_b1[r] >= 0 && n_b1[r] <= M,
+                      "gapro_gp_fit_batch: region %d has M=%d N=%d n_b1=%d", r, M, N, n_b1[r]);
+    }
+    if (check_device() != GAPRO_OK) return GAPRO_ERR_CUDA;
+    GAPRO_CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)n_regions * 4, stream));
+    std::vector<Region> all = sorted_regions(n_regions, train_off, n_b1, test_off);
+    PredictOut po{out_prob, out_conf, out_mu, out_var, out_label, out_mu64, out_var64, status};
+    return run_regions(feats_spp, D, all, train_idx, test_idx, init_noise, iters, 0, lr, jitter_zz, jitter_xx, po, ws,
+                       ws_bytes, true, stream);
+}
+
+extern "C" const char* gapro_gp_debug_layout_names(void) {
+    return "X,Z,Zm,Zv,gZ,Xt,y,m,mm,mv,scal,mu,var,gmu,gv,gsrow,glrow,L,Linv,T,Tm,Tv,GA,GC,Kzx,A,Bm,total,Mp,Np,Wp";
+}
+
+extern "C" int gapro_gp_debug_run(const float* feats_spp, int32_t D, int32_t M, int32_t n_b1, int32_t N,
+                                  const int32_t* train_idx, const int32_t* test_idx, const float* init_noise,
+                                  int32_t iters, int32_t stop_phase, double lr, double jitter_zz, double jitter_xx,
+                                  void* ws, size_t ws_bytes, int64_t* layout, int32_t layout_cap, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    g_launches = 0;
+    GAPRO_REQUIRE(feats_spp && train_idx && test_idx && init_noise && ws && layout, "gapro_gp_debug_run: null pointer");
+    GAPRO_REQUIRE(M >= 1 && N >= 1 && layout_cap >= 31, "gapro_gp_debug_run: bad sizes");
+    std::vector<Region> all(1, make_region(M, N, n_b1, 0, 0, 0));
+    const Layout l = make_layout(all[0].Mp, all[0].Np, all[0].Wp, D);
+    const long long vals[31] = {l.X,  l.Z,   l.Zm,    l.Zv,    l.gZ, l.Xt,   l.y, l.m,  l.mm, l.mv, l.scal,
+                                l.mu, l.var, l.gmu,   l.gv,    l.gsrow, l.glrow, l.L, l.Linv, l.T, l.Tm, l.Tv,
+                                l.GA, l.GC,  l.Kzx,   l.A,     l.Bm, l.total, all[0].Mp, all[0].Np, all[0].Wp};
+    for (int i = 0; i < 31; ++i) layout[i] = vals[i];
+    // status lives at the very end of the workspace for the debug run
+    GAPRO_REQUIRE(ws_bytes >= 64, "gapro_gp_debug_run: workspace too small");
+    int32_t* status = (int32_t*)((char*)ws + ws_bytes - 64);
+    GAPRO_CUDA_TRY(cudaMemsetAsync(status, 0, 4, stream));
+    PredictOut po{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, status};
+    return run_regions(feats_spp, D, all, train_idx, test_idx, init_noise, iters, stop_phase, lr, jitter_zz, jitter_xx,
+                       po, ws, ws_bytes - 64, false, stream);
+}

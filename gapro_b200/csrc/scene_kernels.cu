@@ -1,0 +1,677 @@
+// Scene-level kernels of the gapro_b200 hot path (sm_100a): superpoint densification, floor
+// slab, fused containment + occupancy, feature pooling, index-list compaction, per-superpoint
+// resolution and the broadcast to points.  HBM-bound integer / compare work: no tensor cores.
+#include <cub/cub.cuh>
+
+#include <vector>
+
+#include "common.cuh"
+
+#define FULL_MASK 0xffffffffu
+
+// =============================================================================================
+// U — densification (gen_ps_utils.py:312)
+// =============================================================================================
+__global__ void k_id_minmax(const int64_t* __restrict__ spp_raw, const int64_t* __restrict__ pt_off, int n_scenes,
+                            int64_t n, long long* __restrict__ mn, long long* __restrict__ mx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < n;
+    int sc = 0;
+    long long v = 0;
+    if (valid) {
+        sc = gapro_find_segment<int64_t>(pt_off, n_scenes, i);
+        v = spp_raw[i];
+    }
+    // warp-uniform scene: reduce first, one atomic pair per warp
+    int sc0 = __shfl_sync(FULL_MASK, sc, 0);
+    bool uniform = __all_sync(FULL_MASK, valid && sc == sc0);
+    if (uniform) {
+        long long lo = v, hi = v;
+        for (int o = 16; o; o >>= 1) {
+            long long a = __shfl_xor_sync(FULL_MASK, lo, o), b = __shfl_xor_sync(FULL_MASK, hi, o);
+            lo = a < lo ? a : lo;
+            hi = b > hi ? b : hi;
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(mn + sc, lo);
+            atomicMax(mx + sc, hi);
+        }
+    } else if (valid) {
+        atomicMin(mn + sc, v);
+        atomicMax(mx + sc, v);
+    }
+}
+
+__global__ void k_fill_minmax(long long* mn, long long* mx, int n_scenes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_scenes) {
+        mn[i] = INT64_MAX;
+        mx[i] = INT64_MIN;
+    }
+}
+
+__global__ void k_build_keys(const int64_t* __restrict__ spp_raw, const int64_t* __restrict__ pt_off, int n_scenes,
+                             int64_t n, const long long* __restrict__ mn, int id_bits, uint64_t* __restrict__ keys,
+                             uint32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int sc = gapro_find_segment<int64_t>(pt_off, n_scenes, i);
+    uint64_t rel = (uint64_t)(spp_raw[i] - mn[sc]);
+    keys[i] = ((uint64_t)sc << id_bits) | rel;
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void k_heads(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ head) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    head[k] = (k == 0 || keys[k] != keys[k - 1]) ? 1 : 0;
+}
+
+__global__ void k_densify_finish(const uint64_t* __restrict__ keys, const int32_t* __restrict__ perm,
+                                 const int32_t* __restrict__ head, const int32_t* __restrict__ gsum,
+                                 const int64_t* __restrict__ pt_off, int n_scenes, int64_t n, int id_bits,
+                                 int32_t* __restrict__ spp_gid, int32_t* __restrict__ seg_off,
+                                 int32_t* __restrict__ spp_off_dev) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int g = gsum[k] - 1;
+    spp_gid[perm[k]] = g;
+    if (head[k]) seg_off[g] = (int32_t)k;
+    int sc = (int)(keys[k] >> id_bits);
+    if (k == pt_off[sc]) spp_off_dev[sc] = g;   // first sorted position of scene sc
+    if (k == n - 1) {
+        seg_off[g + 1] = (int32_t)n;
+        spp_off_dev[n_scenes] = g + 1;
+    }
+}
+
+struct DensifyWs {
+    size_t keys_in, keys_out, vals_in, head, gsum, cub_tmp, cub_bytes, minmax, pt_off, spp_off, total;
+};
+
+static DensifyWs densify_layout(int64_t n, int32_t n_scenes) {
+    DensifyWs w;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t r = o;
+        o += gapro_align_up(bytes, 256);
+        return r;
+    };
+    w.keys_in = take(n * 8);
+    w.keys_out = take(n * 8);
+    w.vals_in = take(n * 4);
+    w.head = take(n * 4);
+    w.gsum = take(n * 4);
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n, 0, 64);
+    cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+    w.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+    w.cub_tmp = take(w.cub_bytes);
+    w.minmax = take((size_t)n_scenes * 16);
+    w.pt_off = take((size_t)(n_scenes + 1) * 8);
+    w.spp_off = take((size_t)(n_scenes + 1) * 4);
+    w.total = o;
+    return w;
+}
+
+extern "C" size_t gapro_densify_workspace_bytes(int64_t n_points, int32_t n_scenes) {
+    if (n_points <= 0 || n_scenes <= 0) return 0;
+    return densify_layout(n_points, n_scenes).total;
+}
+
+static int bit_length_u64(uint64_t v) {
+    int b = 0;
+    while (v) {
+        ++b;
+        v >>= 1;
+    }
+    return b;
+}
+
+extern "C" int gapro_densify_spp(const int64_t* spp_raw, const int64_t* pt_off, int32_t n_scenes, int32_t* spp_gid,
+                                 int32_t* perm, int32_t* seg_off, int32_t* spp_off, void* ws, size_t ws_bytes,
+                                 void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GAPRO_REQUIRE(spp_raw && pt_off && spp_gid && perm && seg_off && spp_off && ws, "gapro_densify_spp: null pointer");
+    GAPRO_REQUIRE(n_scenes > 0, "gapro_densify_spp: n_scenes must be positive");
+    int64_t n = pt_off[n_scenes];
+    GAPRO_REQUIRE(pt_off[0] == 0 && n > 0 && n < (int64_t)INT32_MAX, "gapro_densify_spp: bad point offsets (n=%lld)",
+                  (long long)n);
+    for (int s = 0; s < n_scenes; ++s)
+        GAPRO_REQUIRE(pt_off[s + 1] > pt_off[s], "gapro_densify_spp: scene %d has no points", s);
+    DensifyWs w = densify_layout(n, n_scenes);
+    if (ws_bytes < w.total) {
+        gapro_set_error("gapro_densify_spp: workspace %zu < %zu bytes", ws_bytes, w.total);
+        return GAPRO_ERR_WORKSPACE;
+    }
+    char* base = (char*)ws;
+    uint64_t* keys_in = (uint64_t*)(base + w.keys_in);
+    uint64_t* keys_out = (uint64_t*)(base + w.keys_out);
+    uint32_t* vals_in = (uint32_t*)(base + w.vals_in);
+    int32_t* head = (int32_t*)(base + w.head);
+    int32_t* gsum = (int32_t*)(base + w.gsum);
+    long long* mn = (long long*)(base + w.minmax);
+    long long* mx = mn + n_scenes;
+    int64_t* pt_off_dev = (int64_t*)(base + w.pt_off);
+    int32_t* spp_off_dev = (int32_t*)(base + w.spp_off);
+
+    GAPRO_CUDA_TRY(cudaMemcpyAsync(pt_off_dev, pt_off, (size_t)(n_scenes + 1) * 8, cudaMemcpyHostToDevice, stream));
+    const int T = 256;
+    const unsigned G = (unsigned)((n + T - 1) / T);
+    k_fill_minmax<<<(n_scenes + T - 1) / T, T, 0, stream>>>(mn, mx, n_scenes);
+    k_id_minmax<<<G, T, 0, stream>>>(spp_raw, pt_off_dev, n_scenes, n, mn, mx);
+    GAPRO_KERNEL_CHECK();
+    std::vector<long long> h_mm((size_t)2 * n_scenes);
+    GAPRO_CUDA_TRY(cudaMemcpyAsync(h_mm.data(), mn, (size_t)n_scenes * 16, cudaMemcpyDeviceToHost, stream));
+    GAPRO_CUDA_TRY(cudaStreamSynchronize(stream));
+    int id_bits = 1;
+    for (int s = 0; s < n_scenes; ++s) {
+        uint64_t range = (uint64_t)(h_mm[n_scenes + s] - h_mm[s]);
+        int b = bit_length_u64(range);
+        if (b > id_bits) id_bits = b;
+    }
+    int sc_bits = bit_length_u64((uint64_t)(n_scenes - 1));
+    GAPRO_REQUIRE(id_bits <= 40 && id_bits + sc_bits <= 64,
+                  "gapro_densify_spp: superpoint id range needs %d bits (max 40)", id_bits);
+
+    k_build_keys<<<G, T, 0, stream>>>(spp_raw, pt_off_dev, n_scenes, n, mn, id_bits, keys_in, vals_in);
+    GAPRO_KERNEL_CHECK();
+    size_t tmp_bytes = w.cub_bytes;
+    GAPRO_CUDA_TRY(cub::DeviceRadixSort::SortPairs(base + w.cub_tmp, tmp_bytes, keys_in, keys_out, vals_in,
+                                                   (uint32_t*)perm, (int)n, 0, id_bits + sc_bits, stream));
+    k_heads<<<G, T, 0, stream>>>(keys_out, n, head);
+    GAPRO_KERNEL_CHECK();
+    tmp_bytes = w.cub_bytes;
+    GAPRO_CUDA_TRY(cub::DeviceScan::InclusiveSum(base + w.cub_tmp, tmp_bytes, head, gsum, (int)n, stream));
+    k_densify_finish<<<G, T, 0, stream>>>(keys_out, perm, head, gsum, pt_off_dev, n_scenes, n, id_bits, spp_gid,
+                                          seg_off, spp_off_dev);
+    GAPRO_KERNEL_CHECK();
+    GAPRO_CUDA_TRY(cudaMemcpyAsync(spp_off, spp_off_dev, (size_t)(n_scenes + 1) * 4, cudaMemcpyDeviceToHost, stream));
+    GAPRO_CUDA_TRY(cudaStreamSynchronize(stream));
+    return GAPRO_OK;
+}
+
+// =============================================================================================
+// F — floor slab (gen_ps_utils.py:317-326)
+// =============================================================================================
+__device__ __forceinline__ unsigned long long dbl_to_ordered(double d) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_to_dbl(unsigned long long u) {
+    unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void k_extent_init(unsigned long long* scratch, int n_scenes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_scenes * 6) scratch[i] = (i % 6) < 3 ? ~0ull : 0ull;
+}
+
+// one block handles a chunk of 4096 consecutive points; scene looked up per point
+__global__ void k_extent(const double* __restrict__ xyz, const int64_t* __restrict__ pt_off, int n_scenes, int64_t n,
+                         unsigned long long* __restrict__ scratch) {
+    const int PER = 16;
+    int64_t base = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * PER;   // warp's first point
+    int lane = threadIdx.x & 31;
+    int cur = -1;
+    unsigned long long lo[3], hi[3];
+    for (int it = 0; it < PER; ++it) {
+        int64_t i = base + (int64_t)it * 32 + lane;
+        bool valid = i < n;
+        int sc = valid ? gapro_find_segment<int64_t>(pt_off, n_scenes, i) : -2;
+        if (sc != cur) {
+            if (cur >= 0)
+                for (int d = 0; d < 3; ++d) {
+                    atomicMin(scratch + cur * 6 + d, lo[d]);
+                    atomicMax(scratch + cur * 6 + 3 + d, hi[d]);
+                }
+            cur = sc;
+            for (int d = 0; d < 3; ++d) {
+                lo[d] = ~0ull;
+                hi[d] = 0ull;
+            }
+        }
+        if (valid)
+            for (int d = 0; d < 3; ++d) {
+                unsigned long long u = dbl_to_ordered(xyz[3 * i + d]);
+                lo[d] = u < lo[d] ? u : lo[d];
+                hi[d] = u > hi[d] ? u : hi[d];
+            }
+    }
+    // warp-level combine when the whole warp ended in the same scene
+    int c0 = __shfl_sync(FULL_MASK, cur, 0);
+    if (__all_sync(FULL_MASK, cur == c0) && c0 >= 0) {
+        for (int d = 0; d < 3; ++d)
+            for (int o = 16; o; o >>= 1) {
+                unsigned long long a = __shfl_xor_sync(FULL_MASK, lo[d], o), b = __shfl_xor_sync(FULL_MASK, hi[d], o);
+                lo[d] = a < lo[d] ? a : lo[d];
+                hi[d] = b > hi[d] ? b : hi[d];
+            }
+        if (lane == 0)
+            for (int d = 0; d < 3; ++d) {
+                atomicMin(scratch + c0 * 6 + d, lo[d]);
+                atomicMax(scratch + c0 * 6 + 3 + d, hi[d]);
+            }
+    } else if (cur >= 0) {
+        for (int d = 0; d < 3; ++d) {
+            atomicMin(scratch + cur * 6 + d, lo[d]);
+            atomicMax(scratch + cur * 6 + 3 + d, hi[d]);
+        }
+    }
+}
+
+__global__ void k_floor_write(const unsigned long long* __restrict__ scratch, const int32_t* __restrict__ box_off,
+                              int n_scenes, double ground_h, double* __restrict__ boxes, double* __restrict__ vol) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scenes) return;
+    double lo[3], hi[3];
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = ordered_to_dbl(scratch[s * 6 + d]);
+        hi[d] = ordered_to_dbl(scratch[s * 6 + 3 + d]);
+    }
+    int b = box_off[s + 1] - 1;
+    double fb[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], __dadd_rn(lo[2], ground_h)};
+    double v = 1.0;
+    for (int d = 0; d < 3; ++d) {
+        boxes[6 * b + d] = fb[d];
+        boxes[6 * b + 3 + d] = fb[3 + d];
+        double e = __dsub_rn(fb[3 + d], fb[d]);
+        e = e < 0.001 ? 0.001 : e;
+        v = __dmul_rn(v, e);
+    }
+    vol[b] = v;
+}
+
+extern "C" int gapro_floor_boxes(const double* xyz, const int64_t* pt_off_dev, const int32_t* box_off_dev,
+                                 int32_t n_scenes, int64_t n_points, double ground_h, double* boxes,
+                                 double* boxes_vol, uint64_t* scratch, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GAPRO_REQUIRE(xyz && pt_off_dev && box_off_dev && boxes && boxes_vol && scratch, "gapro_floor_boxes: null pointer");
+    GAPRO_REQUIRE(n_scenes > 0 && n_points > 0, "gapro_floor_boxes: empty batch");
+    k_extent_init<<<(n_scenes * 6 + 255) / 256, 256, 0, stream>>>((unsigned long long*)scratch, n_scenes);
+    const int T = 256, PER = 16;
+    unsigned G = (unsigned)((n_points + (int64_t)T * PER - 1) / ((int64_t)T * PER));
+    k_extent<<<G, T, 0, stream>>>(xyz, pt_off_dev, n_scenes, n_points, (unsigned long long*)scratch);
+    k_floor_write<<<(n_scenes + 127) / 128, 128, 0, stream>>>((const unsigned long long*)scratch, box_off_dev, n_scenes,
+                                                               ground_h, boxes, boxes_vol);
+    GAPRO_KERNEL_CHECK();
+    return GAPRO_OK;
+}
+
+// =============================================================================================
+// A + A' — containment + occupancy (gen_ps_utils.py:349-351, 359-363), one warp per superpoint
+// =============================================================================================
+template <int WORDS>
+__global__ void __launch_bounds__(256)
+k_occupancy(const double* __restrict__ xyz, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
+            const int32_t* __restrict__ spp_off, const int32_t* __restrict__ box_off, const double* __restrict__ boxes,
+            int n_scenes, int s_total, double margin, float thresh, uint32_t* __restrict__ occ_bits,
+            int32_t* __restrict__ n_bbs, int32_t* __restrict__ cnt_in, int32_t* __restrict__ excl_cnt,
+            int32_t* __restrict__ inter_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= s_total) return;
+    const int sc = gapro_find_segment<int32_t>(spp_off, n_scenes, g);
+    const int b0 = box_off[sc];
+    const int nb = box_off[sc + 1] - b0;
+    const int start = seg_off[g], end = seg_off[g + 1];
+    int acc[WORDS];
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) acc[w] = 0;
+
+    for (int base = start; base < end; base += 32) {
+        const int k = base + lane;
+        const bool valid = k < end;
+        double x = 0, y = 0, z = 0;
+        if (valid) {
+            const int64_t p = perm[k];
+            x = xyz[3 * p];
+            y = xyz[3 * p + 1];
+            z = xyz[3 * p + 2];
+        }
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) {
+            const int nbw = min(32, nb - 32 * w);
+            uint32_t mask = 0;
+            for (int bb = 0; bb < nbw; ++bb) {
+                const double* bx = boxes + 6 * (size_t)(b0 + 32 * w + bb);   // warp-uniform address: broadcast
+                // margins in float64 on the float64 boxes (gen_ps_utils.py:350)
+                bool in = valid && x >= __dsub_rn(bx[0], margin) && y >= __dsub_rn(bx[1], margin) &&
+                          z >= __dsub_rn(bx[2], margin) && x <= __dadd_rn(bx[3], margin) &&
+                          y <= __dadd_rn(bx[4], margin) && z <= __dadd_rn(bx[5], margin);
+                mask |= (uint32_t)in << bb;
+            }
+            // ballot-transpose: lane bb accumulates the count of box 32w+bb
+            for (int bb = 0; bb < nbw; ++bb) {
+                int c = __popc(__ballot_sync(FULL_MASK, (mask >> bb) & 1u));
+                if (lane == bb) acc[w] += c;
+            }
+        }
+    }
+    const float fcnt = (float)(end - start);
+    uint32_t bits[WORDS];
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < WORDS; ++w) {
+        bool occ = (32 * w + lane < nb) && (__fdiv_rn((float)acc[w], fcnt) >= thresh);
+        bits[w] = __ballot_sync(FULL_MASK, occ);
+        total += __popc(bits[w]);
+        if (cnt_in) cnt_in[((size_t)g * WORDS + w) * 32 + lane] = acc[w];
+        if (lane == 0) occ_bits[(size_t)g * WORDS + w] = bits[w];
+    }
+    if (lane == 0) {
+        n_bbs[g] = total;
+        if (total == 1) {
+#pragma unroll
+            for (int w = 0; w < WORDS; ++w)
+                if (bits[w]) atomicAdd(excl_cnt + b0 + 32 * w + __ffs(bits[w]) - 1, 1);
+        } else if (total >= 2) {
+            const int stride = 32 * WORDS;
+            int32_t* ic = inter_cnt + (size_t)sc * stride * stride;
+#pragma unroll
+            for (int w1 = 0; w1 < WORDS; ++w1) {
+                uint32_t m1 = bits[w1];
+                while (m1) {
+                    int i1 = 32 * w1 + __ffs(m1) - 1;
+                    m1 &= m1 - 1;
+#pragma unroll
+                    for (int w2 = 0; w2 < WORDS; ++w2) {
+                        if (w2 < w1) continue;
+                        uint32_t m2 = bits[w2];
+                        while (m2) {
+                            int i2 = 32 * w2 + __ffs(m2) - 1;
+                            m2 &= m2 - 1;
+                            if (i2 > i1) atomicAdd(ic + (size_t)i1 * stride + i2, 1);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+extern "C" int gapro_occupancy(const double* xyz, const int32_t* perm, const int32_t* seg_off,
+                               const int32_t* spp_off_dev, const int32_t* box_off_dev, const double* boxes,
+                               int32_t n_scenes, int32_t s_total, int32_t n_boxes, int32_t words, double margin,
+                               float thresh, uint32_t* occ_bits, int32_t* n_bbs, int32_t* cnt_in, int32_t* excl_cnt,
+                               int32_t* inter_cnt, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GAPRO_REQUIRE(xyz && perm && seg_off && spp_off_dev && box_off_dev && boxes && occ_bits && n_bbs && excl_cnt &&
+                      inter_cnt,
+                  "gapro_occupancy: null pointer");
+    GAPRO_REQUIRE(n_scenes > 0 && s_total > 0 && n_boxes > 0, "gapro_occupancy: empty batch");
+    GAPRO_REQUIRE(words == 1 || words == 2 || words == 4 || words == 8,
+                  "gapro_occupancy: words must be 1, 2, 4 or 8 (got %d; at most 256 boxes per scene)", words);
+    GAPRO_CUDA_TRY(cudaMemsetAsync(excl_cnt, 0, (size_t)n_boxes * 4, stream));
+    GAPRO_CUDA_TRY(cudaMemsetAsync(inter_cnt, 0, (size_t)n_scenes * 32 * words * 32 * words * 4, stream));
+    const int T = 256, WPB = T / 32;
+    unsigned G = (unsigned)((s_total + WPB - 1) / WPB);
+#define LAUNCH_OCC(W)                                                                                              \
+    k_occupancy<W><<<G, T, 0, stream>>>(xyz, perm, seg_off, spp_off_dev, box_off_dev, boxes, n_scenes, s_total,    \
+                                        margin, thresh, occ_bits, n_bbs, cnt_in, excl_cnt, inter_cnt)
+    switch (words) {
+        case 1: LAUNCH_OCC(1); break;
+        case 2: LAUNCH_OCC(2); break;
+        case 4: LAUNCH_OCC(4); break;
+        default: LAUNCH_OCC(8); break;
+    }
+#undef LAUNCH_OCC
+    GAPRO_KERNEL_CHECK();
+    return GAPRO_OK;
+}
+
+// =============================================================================================
+// B — feature pooling (gen_ps_utils.py:357): float32 sum in point-index order, / float32 count
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+k_pool_feats(const float* __restrict__ feats, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
+             int s_total, int D, float* __restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)s_total * D) return;
+    const int g = (int)(t / D), d = (int)(t % D);
+    const int start = seg_off[g], end = seg_off[g + 1];
+    float acc = 0.0f;
+    int k = start;
+    for (; k + 4 <= end; k += 4) {     // four independent gathers in flight, adds strictly in order
+        float v0 = feats[(int64_t)perm[k] * D + d];
+        float v1 = feats[(int64_t)perm[k + 1] * D + d];
+        float v2 = feats[(int64_t)perm[k + 2] * D + d];
+        float v3 = feats[(int64_t)perm[k + 3] * D + d];
+        acc = __fadd_rn(acc, v0);
+        acc = __fadd_rn(acc, v1);
+        acc = __fadd_rn(acc, v2);
+        acc = __fadd_rn(acc, v3);
+    }
+    for (; k < end; ++k) acc = __fadd_rn(acc, feats[(int64_t)perm[k] * D + d]);
+    out[t] = __fdiv_rn(acc, (float)(end - start));
+}
+
+extern "C" int gapro_pool_feats(const float* feats, const int32_t* perm, const int32_t* seg_off, int32_t s_total,
+                                int32_t D, float* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GAPRO_REQUIRE(feats && perm && seg_off && out, "gapro_pool_feats: null pointer");
+    GAPRO_REQUIRE(s_total > 0 && D > 0, "gapro_pool_feats: empty input");
+    int64_t total = (int64_t)s_total * D;
+    k_pool_feats<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(feats, perm, seg_off, s_total, D, out);
+    GAPRO_KERNEL_CHECK();
+    return GAPRO_OK;
+}
+
+// =============================================================================================
+// Index lists by warp-ballot compaction (torch.nonzero at gen_ps_utils.py:405, 428-429)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+k_compact_lists(const uint32_t* __restrict__ occ_bits, const int32_t* __restrict__ n_bbs,
+                const int32_t* __restrict__ spp_off, int words, const int32_t* __restrict__ list_scene,
+                const int32_t* __restrict__ list_b1, const int32_t* __restrict__ list_b2,
+                const int32_t* __restrict__ list_off, int32_t* __restrict__ out_idx) {
+    __shared__ int warp_cnt[8];
+    __shared__ int running;
+    const int l = blockIdx.x;
+    const int sc = list_scene[l], b1 = list_b1[l], b2 = list_b2[l];
+    const int g0 = spp_off[sc], g1 = spp_off[sc + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t* out = out_idx + list_off[l];
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (int base = g0; base < g1; base += 256) {
+        const int g = base + threadIdx.x;
+        bool keep = false;
+        if (g < g1) {
+            const uint32_t* row = occ_bits + (size_t)g * words;
+            bool in1 = (row[b1 >> 5] >> (b1 & 31)) & 1u;
+            keep = b2 < 0 ? (in1 && n_bbs[g] == 1) : (in1 && ((row[b2 >> 5] >> (b2 & 31)) & 1u));
+        }
+        const uint32_t bal = __ballot_sync(FULL_MASK, keep);
+        if (lane == 0) warp_cnt[wid] = __popc(bal);
+        __syncthreads();
+        int before = running;
+        for (int w = 0; w < wid; ++w) before += warp_cnt[w];
+        if (keep) out[before + __popc(bal & ((1u << lane) - 1u))] = g;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += warp_cnt[w];
+            running += tot;
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int gapro_compact_lists(const uint32_t* occ_bits, const int32_t* n_bbs, const int32_t* spp_off_dev,
+                                   int32_t words, const int32_t* list_scene, const int32_t* list_b1,
+                                   const int32_t* list_b2, const int32_t* list_off, int32_t n_lists, int32_t* out_idx,
+                                   void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_lists == 0) return GAPRO_OK;
+    GAPRO_REQUIRE(occ_bits && n_bbs && spp_off_dev && list_scene && list_b1 && list_b2 && list_off && out_idx,
+                  "gapro_compact_lists: null pointer");
+    GAPRO_REQUIRE(n_lists > 0 && words > 0, "gapro_compact_lists: bad sizes");
+    k_compact_lists<<<n_lists, 256, 0, stream>>>(occ_bits, n_bbs, spp_off_dev, words, list_scene, list_b1, list_b2,
+                                                 list_off, out_idx);
+    GAPRO_KERNEL_CHECK();
+    return GAPRO_OK;
+}
+
+// =============================================================================================
+// S0 + M + D + per-superpoint labels (gen_ps_utils.py:365-383, 412-446, 450-476): one CTA / scene
+// =============================================================================================
+__global__ void __launch_bounds__(512)
+k_resolve_spp(const uint32_t* __restrict__ occ_bits, const int32_t* __restrict__ n_bbs, int words,
+              const int32_t* __restrict__ spp_off, const int32_t* __restrict__ box_off,
+              const double* __restrict__ boxes_vol, const int64_t* __restrict__ boxes_cls,
+              const int32_t* __restrict__ n_fg, int instance_classes, const int32_t* __restrict__ ev_off,
+              const int32_t* __restrict__ ev_kind, const int32_t* __restrict__ ev_b1, const int32_t* __restrict__ ev_b2,
+              const int32_t* __restrict__ ev_list_off, const int32_t* __restrict__ ev_list_len,
+              const int32_t* __restrict__ ev_gp_off, const int32_t* __restrict__ lists_idx,
+              const float* __restrict__ gp_conf, const uint8_t* __restrict__ gp_label, const float* __restrict__ gp_mu,
+              const float* __restrict__ gp_var, int32_t* __restrict__ sem_spp, int32_t* __restrict__ inst_spp,
+              float* __restrict__ prob_spp, float* __restrict__ mu_spp, float* __restrict__ var_spp) {
+    const int sc = blockIdx.x;
+    const int g0 = spp_off[sc], g1 = spp_off[sc + 1];
+    const int b0 = box_off[sc];
+    // S0: trivial assignment (:365-383).  inst == -100 doubles as "undetermined".
+    for (int g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
+        const int nb = n_bbs[g];
+        int inst = -100;
+        float prob = 0.0f;
+        if (nb == 1) {
+            for (int w = 0; w < words; ++w) {
+                uint32_t b = occ_bits[(size_t)g * words + w];
+                if (b) inst = 32 * w + __ffs(b) - 1;
+            }
+            prob = 1.0f;
+        } else if (nb == 0) {
+            inst = -1;
+            prob = 1.0f;
+        }
+        inst_spp[g] = inst;
+        prob_spp[g] = prob;
+        mu_spp[g] = -100.0f;
+        var_spp[g] = -100.0f;
+    }
+    __syncthreads();
+    // M: events in loop order (:411-446)
+    for (int e = ev_off[sc]; e < ev_off[sc + 1]; ++e) {
+        const int kind = ev_kind[e], b1 = ev_b1[e], b2 = ev_b2[e];
+        const int32_t* list = lists_idx + ev_list_off[e];
+        const int len = ev_list_len[e];
+        const int gp = ev_gp_off[e];
+        for (int r = threadIdx.x; r < len; r += blockDim.x) {
+            const int g = list[r];
+            if (kind == GAPRO_EV_GP) {
+                const float conf = gp_conf[gp + r];
+                if (prob_spp[g] < conf) {                      // strict, float32 (:438)
+                    inst_spp[g] = gp_label[gp + r] ? b2 : b1;   // :440-441
+                    prob_spp[g] = conf;
+                    mu_spp[g] = gp_mu[gp + r];
+                    var_spp[g] = gp_var[gp + r];
+                }
+            } else {
+                inst_spp[g] = (kind == GAPRO_EV_NEST_B1) ? b1 : b2;
+                prob_spp[g] = 1.0f;
+            }
+        }
+        __syncthreads();
+    }
+    // D: smallest-volume fallback (:450-464) and per-superpoint labels (:467-476)
+    const int nfg = n_fg[sc];
+    for (int g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
+        int inst = inst_spp[g];
+        if (n_bbs[g] > 1 && inst == -100) {
+            double best = 0.0;
+            int arg = -1;
+            for (int w = 0; w < words; ++w) {
+                uint32_t m = occ_bits[(size_t)g * words + w];
+                while (m) {
+                    int b = 32 * w + __ffs(m) - 1;
+                    m &= m - 1;
+                    double v = boxes_vol[b0 + b];
+                    if (arg < 0 || v < best) {
+                        best = v;
+                        arg = b;
+                    }
+                }
+            }
+            inst = arg;
+            prob_spp[g] = 1.0f;
+        }
+        int sem = -100, inst_out = -100;
+        if (inst >= 0) {
+            sem = (int)boxes_cls[b0 + inst];
+            inst_out = inst;
+        } else if (inst == -1) {
+            sem = instance_classes;
+        }
+        if (inst_out >= nfg) inst_out = -100;
+        sem_spp[g] = sem;
+        inst_spp[g] = inst_out;
+    }
+}
+
+extern "C" int gapro_resolve_spp(const uint32_t* occ_bits, const int32_t* n_bbs, int32_t words,
+                                 const int32_t* spp_off_dev, const int32_t* box_off_dev, const double* boxes_vol,
+                                 const int64_t* boxes_cls, const int32_t* n_fg, int32_t instance_classes,
+                                 int32_t n_scenes, const int32_t* ev_off, const int32_t* ev_kind, const int32_t* ev_b1,
+                                 const int32_t* ev_b2, const int32_t* ev_list_off, const int32_t* ev_list_len,
+                                 const int32_t* ev_gp_off, const int32_t* lists_idx, const float* gp_conf,
+                                 const uint8_t* gp_label, const float* gp_mu, const float* gp_var, int32_t* sem_spp,
+                                 int32_t* inst_spp, float* prob_spp, float* mu_spp, float* var_spp, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GAPRO_REQUIRE(occ_bits && n_bbs && spp_off_dev && box_off_dev && boxes_vol && boxes_cls && n_fg && ev_off &&
+                      sem_spp && inst_spp && prob_spp && mu_spp && var_spp,
+                  "gapro_resolve_spp: null pointer");
+    GAPRO_REQUIRE(n_scenes > 0 && words > 0, "gapro_resolve_spp: bad sizes");
+    k_resolve_spp<<<n_scenes, 512, 0, stream>>>(occ_bits, n_bbs, words, spp_off_dev, box_off_dev, boxes_vol, boxes_cls,
+                                                n_fg, instance_classes, ev_off, ev_kind, ev_b1, ev_b2, ev_list_off,
+                                                ev_list_len, ev_gp_off, lists_idx, gp_conf, gp_label, gp_mu, gp_var,
+                                                sem_spp, inst_spp, prob_spp, mu_spp, var_spp);
+    GAPRO_KERNEL_CHECK();
+    return GAPRO_OK;
+}
+
+// =============================================================================================
+// E — broadcast to points (gen_ps_utils.py:478-480)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+k_broadcast(const int32_t* __restrict__ spp_gid, int64_t n, const int32_t* __restrict__ sem_spp,
+            const int32_t* __restrict__ inst_spp, const float* __restrict__ prob_spp, int32_t* __restrict__ sem,
+            int32_t* __restrict__ inst, float* __restrict__ prob) {
+    // 4 points per thread, 128-bit loads/stores (n4 quads) + scalar tail
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t n4 = n >> 2;
+    if (q < n4) {
+        int4 g = reinterpret_cast<const int4*>(spp_gid)[q];
+        int4 s = make_int4(sem_spp[g.x], sem_spp[g.y], sem_spp[g.z], sem_spp[g.w]);
+        int4 i = make_int4(inst_spp[g.x], inst_spp[g.y], inst_spp[g.z], inst_spp[g.w]);
+        float4 p = make_float4(prob_spp[g.x], prob_spp[g.y], prob_spp[g.z], prob_spp[g.w]);
+        reinterpret_cast<int4*>(sem)[q] = s;
+        reinterpret_cast<int4*>(inst)[q] = i;
+        reinterpret_cast<float4*>(prob)[q] = p;
+    } else if (q == n4) {
+        for (int64_t k = n4 << 2; k < n; ++k) {
+            int g = spp_gid[k];
+            sem[k] = sem_spp[g];
+            inst[k] = inst_spp[g];
+            prob[k] = prob_spp[g];
+        }
+    }
+}
+
+extern "C" int gapro_broadcast_labels(const int32_t* spp_gid, int64_t n_points, const int32_t* sem_spp,
+                                      const int32_t* inst_spp, const float* prob_spp, int32_t* sem, int32_t* inst,
+                                      float* prob, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GAPRO_REQUIRE(spp_gid && sem_spp && inst_spp && prob_spp && sem && inst && prob, "gapro_broadcast_labels: null pointer");
+    GAPRO_REQUIRE(n_points > 0, "gapro_broadcast_labels: empty input");
+    GAPRO_REQUIRE(((uintptr_t)spp_gid % 16 == 0) && ((uintptr_t)sem % 16 == 0) && ((uintptr_t)inst % 16 == 0) &&
+                      ((uintptr_t)prob % 16 == 0),
+                  "gapro_broadcast_labels: point arrays must be 16-byte aligned");
+    int64_t threads = (n_points >> 2) + 1;
+    k_broadcast<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(spp_gid, n_points, sem_spp, inst_spp, prob_spp,
+                                                                       sem, inst, prob);
+    GAPRO_KERNEL_CHECK();
+    return GAPRO_OK;
+}
