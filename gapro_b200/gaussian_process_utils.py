@@ -1,0 +1,106 @@
+"""Host-side mirror of /root/reference/gapro/gaussian_process_utils.py for the GP region fit.
+
+`fit_gp_spp` keeps the reference signature and return tuple; `fit_gp_regions` is the batched
+form the pipeline uses.  The model the reference builds with gpytorch
+(GPClassificationModel, gaussian_process_utils.py:11-25: whitened VariationalStrategy with a
+CholeskyVariationalDistribution over M inducing points initialised at the training rows,
+ConstantMean, ScaleKernel(RBFKernel), BernoulliLikelihood, VariationalELBO, Adam lr 0.1) is
+implemented in libgapro_b200.so (csrc/gp_fit.cu); nothing here does arithmetic.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ["fit_gp_spp", "fit_gp_regions"]
+
+
+def fit_gp_regions(feats_spp, train_lists, n_b1, test_lists, init_noise=None, training_iter=50, lr=0.1,
+                   jitter_zz=1e-4, jitter_xx=1e-4, workspace_bytes=None, return_float64=False):
+    """Fit R independent regions in one batched call.
+
+    feats_spp   (S,D) float32 CUDA tensor of pooled superpoint features
+    train_lists list of R int tensors/arrays: training rows (box-1 rows first)
+    n_b1        list of R ints: how many leading training rows belong to box 1 (label -1)
+    test_lists  list of R int tensors/arrays: rows to predict
+    init_noise  list of R float arrays of standard-normal draws (None: torch.randn on device)
+    Returns a list of R tuples (pred_probs, pred_probs_new, pred_labels, pred_mu, pred_variance)
+    (+ (mu64, var64) when return_float64)."""
+    if not feats_spp.is_cuda:
+        raise _lib.GaproError("fit_gp_regions needs CUDA tensors; gapro_b200 has no CPU fallback")
+    lib = _lib.load()
+    dev = feats_spp.device
+    feats = feats_spp.float().contiguous()
+    R = len(train_lists)
+    if R == 0:
+        return []
+    as_np = lambda x: (x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)).astype(np.int32).reshape(-1)
+    tr = [as_np(t) for t in train_lists]
+    te = [as_np(t) for t in test_lists]
+    train_off = np.zeros(R + 1, dtype=np.int32)
+    train_off[1:] = np.cumsum([len(t) for t in tr])
+    test_off = np.zeros(R + 1, dtype=np.int32)
+    test_off[1:] = np.cumsum([len(t) for t in te])
+    nb1 = np.asarray(n_b1, dtype=np.int32)
+    D = int(feats.shape[1])
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    train_idx = to_dev(np.concatenate(tr))
+    test_idx = to_dev(np.concatenate(te))
+    if init_noise is None:
+        noise = torch.randn(int(train_off[-1]), dtype=torch.float32, device=dev)
+    else:
+        noise = to_dev(np.concatenate([np.asarray(z, dtype=np.float32).reshape(-1) for z in init_noise]))
+        if noise.numel() != int(train_off[-1]):
+            raise ValueError("init_noise must hold one draw per training row")
+    nt = int(test_off[-1])
+    prob = torch.empty(nt, dtype=torch.float32, device=dev)
+    conf = torch.empty_like(prob)
+    mu = torch.empty_like(prob)
+    var = torch.empty_like(prob)
+    label = torch.empty(nt, dtype=torch.uint8, device=dev)
+    mu64 = torch.empty(nt, dtype=torch.float64, device=dev) if return_float64 else None
+    var64 = torch.empty(nt, dtype=torch.float64, device=dev) if return_float64 else None
+    status = torch.zeros(R, dtype=torch.int32, device=dev)
+    full = lib.gapro_gp_workspace_bytes(R, train_off.ctypes.data, test_off.ctypes.data, D)
+    need = lib.gapro_gp_min_workspace_bytes(R, train_off.ctypes.data, test_off.ctypes.data, D)
+    nbytes = full if workspace_bytes is None else max(min(full, int(workspace_bytes)), need)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    p = lambda t: 0 if t is None else t.data_ptr()
+    _lib.check(lib.gapro_gp_fit_batch(feats.data_ptr(), D, R, train_off.ctypes.data, nb1.ctypes.data,
+                                      test_off.ctypes.data, train_idx.data_ptr(), test_idx.data_ptr(),
+                                      noise.data_ptr(), int(training_iter), float(lr), float(jitter_zz),
+                                      float(jitter_xx), prob.data_ptr(), conf.data_ptr(), label.data_ptr(),
+                                      mu.data_ptr(), var.data_ptr(), p(mu64), p(var64), status.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), stream), "gapro_gp_fit_batch")
+    st = status.cpu().numpy()
+    if np.any(st & _lib.GP_NOT_PSD):
+        raise _lib.GaproError("NotPSDError: K_ZZ not positive definite in region %d" % int(np.flatnonzero(st & 1)[0]))
+    if np.any(st & _lib.GP_NAN):
+        raise _lib.GaproError("NanError: non-finite GP posterior")
+    out = []
+    for r in range(R):
+        a, b = int(test_off[r]), int(test_off[r + 1])
+        item = (prob[a:b], conf[a:b], label[a:b].bool(), mu[a:b], var[a:b])
+        if return_float64:
+            item = item + (mu64[a:b], var64[a:b])
+        out.append(item)
+    return out
+
+
+def fit_gp_spp(coords_float_spp, feats_spp, b1_inds, b2_inds, intersect_inds, training_iter=50, *, init_noise=None):
+    """Drop-in for fit_gp_spp (/root/reference/gapro/gaussian_process_utils.py:382-445).
+
+    Trains on feats_spp[b1_inds] (label -1) and feats_spp[b2_inds] (label +1), predicts at
+    feats_spp[intersect_inds]; returns (pred_probs, pred_probs_new, pred_labels, pred_mu,
+    pred_variance), each of length len(intersect_inds).  `coords_float_spp` is accepted and
+    unused, as in the reference (:385-392).  `init_noise` (M standard-normal draws) replaces
+    gpytorch's unseeded random initialisation of the variational mean."""
+    b1 = b1_inds.reshape(-1)
+    b2 = b2_inds.reshape(-1)
+    train = torch.cat([b1, b2])
+    res = fit_gp_regions(feats_spp, [train], [int(b1.numel())], [intersect_inds],
+                         init_noise=None if init_noise is None else [init_noise], training_iter=training_iter)
+    return res[0]

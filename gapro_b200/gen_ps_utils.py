@@ -1,0 +1,123 @@
+"""Host-side mirror of /root/reference/gapro/gen_ps_utils.py for the GP pseudo-label path.
+
+Same call surface as the reference (names, argument meaning, return arity, dtypes,
+shapes — including the per-superpoint `mu`/`var` of gen_ps_utils.py:482), backed by the
+CUDA library through `gapro_b200.engine`.  Everything here is host orchestration; the
+arithmetic runs in libgapro_b200.so.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import SceneInputs, get_engine
+
+__all__ = ["gen_pseudo_label_gaussian_process", "gen_pseudo_labels_batch", "getInstanceInfo", "batch_giou_cross",
+           "is_box1_in_box2", "is_within_bb_torch", "SceneInputs"]
+
+
+def gen_pseudo_label_gaussian_process(
+    coords_float,
+    mask_feats,
+    spp,
+    instance_cls,
+    instance_box,
+    instance_box_volume,
+    wall_box,
+    wall_box_volume,
+    instance_classes=18,
+    dataset_name="scannetv2",
+    ground_h=0.1,
+    training_iter=50,
+    thresh_spp_occu=0.8,
+    *,
+    noise_seed=None,
+    jitter_zz=1e-4,
+    return_debug=False,
+):
+    """Drop-in for gen_pseudo_label_gaussian_process (/root/reference/gapro/gen_ps_utils.py:293-482).
+
+    Returns (ps_semantic_label[N] int32, ps_instance_label[N] int32, ps_prob_label[N] float32,
+    ps_mu_label[S] float32, ps_variance_label[S] float32) on the device of `coords_float`.
+    `dataset_name` is accepted and unused, as in the reference.  Keyword-only extras:
+    `noise_seed` makes the GP initialisation reproducible (the reference draws it from the
+    unseeded global RNG inside gpytorch); `jitter_zz` is gpytorch's K_ZZ jitter (1e-4 since
+    gpytorch 1.6, 1e-3 before)."""
+    eng = get_engine(coords_float.device if coords_float.is_cuda else None)
+    scene = SceneInputs(coords_float, mask_feats, spp, instance_cls, instance_box, instance_box_volume,
+                        wall_box, wall_box_volume, noise_seed=noise_seed)
+    res = eng.run([scene], instance_classes=instance_classes, ground_h=ground_h, training_iter=training_iter,
+                  thresh_spp_occu=thresh_spp_occu, jitter_zz=jitter_zz, debug=return_debug, want_cnt_in=return_debug)
+    if return_debug:
+        return res[0][0], res[1]
+    return res[0]
+
+
+def gen_pseudo_labels_batch(scenes, instance_classes=18, ground_h=0.1, training_iter=50, thresh_spp_occu=0.8,
+                            jitter_zz=1e-4, device=None, return_debug=False):
+    """Many scenes through ONE pass of the hot path (scenes are independent: gen_ps.py:36).
+    `scenes` is a sequence of SceneInputs; returns one 5-tuple per scene."""
+    eng = get_engine(device)
+    return eng.run(list(scenes), instance_classes=instance_classes, ground_h=ground_h, training_iter=training_iter,
+                   thresh_spp_occu=thresh_spp_occu, jitter_zz=jitter_zz, debug=return_debug)
+
+
+# --------------------------------------------------------------------------------------------
+# host helpers of the reference's call surface
+# --------------------------------------------------------------------------------------------
+def getInstanceInfo(xyz, instance_label, semantic_label, dataset_name="scannetv2"):
+    """Per-instance axis-aligned boxes from labelled points — same contract as
+    getInstanceInfo (/root/reference/gapro/gen_ps_utils.py:195-239): instances are listed in
+    increasing GT id with empty ids skipped, class = semantic label of the instance's first
+    point (minus 2 for scannetv2 unless -100), volume = prod(clip(max-min, 0)); returns None
+    when there is no instance.  Vectorised (one stable sort) instead of a per-instance scan."""
+    xyz = np.asarray(xyz)
+    inst = np.asarray(instance_label)
+    sem = np.asarray(semantic_label)
+    instance_num = int(inst.max()) + 1
+    corners_label = np.full((xyz.shape[0], 6), -100.0, dtype=np.float32)
+    idx = np.flatnonzero((inst >= 0) & (inst == np.floor(inst)))
+    if idx.size == 0:
+        return None
+    ids = inst[idx].astype(np.int64)
+    order = np.argsort(ids, kind="stable")
+    idx, ids = idx[order], ids[order]
+    starts = np.flatnonzero(np.r_[True, ids[1:] != ids[:-1]])
+    pts = xyz[idx]
+    lo = np.minimum.reduceat(pts, starts, axis=0)
+    hi = np.maximum.reduceat(pts, starts, axis=0)
+    seg = np.cumsum(np.r_[True, ids[1:] != ids[:-1]]) - 1
+    corners_label[idx, :3] = lo[seg] - pts
+    corners_label[idx, 3:] = hi[seg] - pts
+    instance_cls = np.array(sem[idx[starts]])
+    instance_box = np.concatenate([lo, hi], axis=1)
+    ext = np.clip(hi - lo, 0.0, None)
+    instance_box_volume = ext[:, 0] * ext[:, 1] * ext[:, 2]
+    if dataset_name == "scannetv2":
+        instance_cls[instance_cls != -100] -= 2
+    return instance_num, instance_cls, instance_box, instance_box_volume, corners_label
+
+
+def batch_giou_cross(boxes1, boxes2):
+    """IoU / GIoU of every box of `boxes1` (N,6) with every box of `boxes2` (M,6) — the
+    formulas of /root/reference/gapro/gen_ps_utils.py:33-61 (1e-6 in both denominators)."""
+    a, b = boxes1[:, None, :], boxes2[None, :, :]
+    inter = (torch.minimum(a[..., 3:], b[..., 3:]) - torch.maximum(a[..., :3], b[..., :3])).clamp(min=0.0).prod(-1)
+    va = (a[..., 3:] - a[..., :3]).clamp(min=0.0).prod(-1)
+    vb = (b[..., 3:] - b[..., :3]).clamp(min=0.0).prod(-1)
+    union = va + vb - inter
+    iou = inter / (union + 1e-6)
+    hull = (torch.maximum(a[..., 3:], b[..., 3:]) - torch.minimum(a[..., :3], b[..., :3])).clamp(min=0.0).prod(-1)
+    return iou, iou - (hull - union) / (hull + 1e-6)
+
+
+def is_box1_in_box2(box1, box2, offset=0.05):
+    """/root/reference/gapro/gen_ps_utils.py:75-76."""
+    return torch.all((box1[:3] + offset) >= box2[:3]) & torch.all((box1[3:] - offset) <= box2[3:])
+
+
+def is_within_bb_torch(points, bb_min, bb_max):
+    """/root/reference/gapro/gen_ps_utils.py:79-80 (kept for API parity; the hot path uses the
+    fused CUDA containment kernel, not this)."""
+    return torch.all(points >= bb_min, dim=-1) & torch.all(points <= bb_max, dim=-1)
