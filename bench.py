@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""Benchmark of the pseudo-label generator hot path (BASELINE.json metric: scenes/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the whole hot path over one batch of synthetic ScanNet-shaped scenes
+per GPU (configs[2] of BASELINE.json: scenes of the 1201-scene ScanNetv2-train-shaped set,
+N ~ U(50k, 250k) points); scenes shard across ranks with no data-path collective (weak
+scaling), one final NCCL gather of label metadata.  Prints ONE JSON line on rank 0.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, gpytorch precision
+policy: float32 everywhere, float64 Cholesky + solve) on the host cores — the reference itself
+cannot be installed here (gpytorch and torch_scatter are absent).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scenes/sec pseudo-labelled"
+WORKLOAD = "c3: ScanNetv2-train-shaped synthetic scenes (N~U(50k,250k) pts, 12-40 boxes + 4 walls + floor, D=6), %d scenes/GPU/step"
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def make_inputs(rank, n_scenes, workload):
+    from gapro_b200 import synthetic
+    from gapro_b200.gen_ps import synthetic_inputs
+    inps = []
+    for i in range(n_scenes):
+        idx = rank * n_scenes + i
+        cfg = synthetic.c3_config(idx) if workload == "c3" else synthetic.CONFIGS[workload]
+        inps.append(synthetic_inputs(synthetic.make_scene(1000 + idx, cfg), use_deepfeat=cfg.feat_dim == 32))
+    return inps
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle with the reference's precision policy, regions spread over all host cores
+# ------------------------------------------------------------------------------------------------
+def _warm_worker():
+    """Pool initializer: absorb torch's one-off first-call cost (seconds) outside the timed region."""
+    import torch as _t
+    from oracle import gp_oracle
+    _t.set_num_threads(1)
+    r = np.random.default_rng(0)
+    gp_oracle.fit_region_autograd(r.normal(size=(6, 3)).astype(np.float32), 3, r.normal(size=(2, 3)).astype(np.float32),
+                                  r.normal(size=6).astype(np.float32), iters=2, policy="gpytorch")
+
+
+def _fit_one(job):
+    import torch as _t
+    from oracle import gp_oracle
+    _t.set_num_threads(1)
+    X, n1, Xt, nz = job
+    t0 = time.perf_counter()
+    gp_oracle.fit_region_autograd(X, n1, Xt, nz, policy="gpytorch")
+    return time.perf_counter() - t0
+
+
+def cpu_scene_time(inp, budget_s, pool, n_workers):
+    """Wall-clock seconds the CPU path needs for one scene: stages + GP regions over a process
+    pool.  Regions are run in loop order until `budget_s` is spent; the rest is extrapolated by
+    sum(M^3).  Returns (seconds, description)."""
+    from oracle import gen_ps_oracle as O
+    jobs = []
+
+    def record(X, n1, Xt, nz):
+        jobs.append((np.array(X), n1, np.array(Xt), np.array(nz)))
+        n = len(Xt)
+        return dict(conf=np.full(n, 0.75, np.float32), label=np.ones(n, bool), mu=np.zeros(n, np.float32),
+                    var=np.ones(n, np.float32))
+
+    t0 = time.perf_counter()
+    O.gen_pseudo_label_oracle(inp["xyz"], inp["mask_feats"].astype(np.float32), inp["spp"],
+                              inp["instance_cls"].astype(np.int64), inp["instance_box"].astype(np.float32),
+                              inp["instance_box_volume"].astype(np.float32), inp["wall_box"], inp["wall_volume"],
+                              thresh_spp_occu=0.999, fit_fn=record)
+    t_stage = time.perf_counter() - t0
+    m3 = np.array([float(len(j[0])) ** 3 for j in jobs])
+    done, t_reg = 0, 0.0
+    group = max(n_workers * 2, 1)
+    while done < len(jobs) and t_reg < budget_s:
+        t1 = time.perf_counter()
+        list(pool.imap_unordered(_fit_one, jobs[done:done + group]))
+        t_reg += time.perf_counter() - t1
+        done += min(group, len(jobs) - done)
+    frac = m3[:done].sum() / m3.sum() if len(jobs) else 1.0
+    total = t_stage + (t_reg / frac if frac > 0 else 0.0)
+    desc = (f"1 scene of the batch (N={len(inp['xyz'])}): stages timed in full, first {done} of {len(jobs)} GP regions "
+            f"timed ({100 * frac:.0f}% of sum M^3) on a {n_workers}-process pool, remainder extrapolated by sum M^3")
+    return total, desc
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    n_workers = len(os.sched_getaffinity(0))
+    inp = make_inputs(0, 1, args.workload)[0]
+    budget = max(3.0, min(25.0, 150.0 / max(args.steps + args.warmup, 1)))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(n_workers, initializer=_warm_worker) as pool:
+        times = []
+        desc = ""
+        for s in range(args.warmup + args.steps):
+            t, desc = cpu_scene_time(inp, budget, pool, n_workers)
+            if s >= args.warmup:
+                times.append(t)
+    sec = float(np.mean(times))
+    val = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "scenes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 Cholesky/solve), CPU", "data": "synthetic",
+        "config": {"workload": WORKLOAD % args.scenes, "note": "CPU restatement (oracle/, gpytorch policy); "
+                   "the reference itself needs gpytorch + torch_scatter, not installable here"},
+        "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": n_workers, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def stage_rooflines(eng, lib, stream, flush):
+    """HBM-bound stages timed alone with CUDA events on the batch left in eng.last."""
+    from gapro_b200 import _lib
+    L = eng.last
+    peak, peak_src = hbm_peak()
+    N, S, Bt, D, words = L["N"], L["St"], L["Bt"], L["D"], L["words"]
+
+    def time_it(fn, reps=5):
+        ts = []
+        for _ in range(reps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    occ = lambda: _lib.check(lib.gapro_occupancy(
+        L["xyz"].data_ptr(), L["perm"].data_ptr(), L["seg_off"].data_ptr(), L["spp_off_dev"].data_ptr(),
+        L["box_off_dev"].data_ptr(), L["boxes"].data_ptr(), L["ns"], S, Bt, words, 0.005, L["thresh"],
+        L["occ_bits"].data_ptr(), L["n_bbs"].data_ptr(), 0, L["excl_cnt"].data_ptr(), L["inter_cnt"].data_ptr(), stream), "occ")
+    pool = lambda: _lib.check(lib.gapro_pool_feats(L["feats"].data_ptr(), L["perm"].data_ptr(), L["seg_off"].data_ptr(),
+                                                   S, D, L["feats_spp"].data_ptr(), stream), "pool")
+    bc = lambda: _lib.check(lib.gapro_broadcast_labels(L["spp_gid"].data_ptr(), N, L["sem_spp"].data_ptr(),
+                                                       L["inst_spp"].data_ptr(), L["prob_spp"].data_ptr(),
+                                                       L["sem"].data_ptr(), L["inst"].data_ptr(), L["prob"].data_ptr(),
+                                                       stream), "bcast")
+    out = {}
+    for name, fn, nbytes in (
+        ("containment+occupancy (A+A')", occ, N * (24 + 4) + 48 * Bt + 4 * S * words + 4 * S),
+        ("feature pooling (B)", pool, N * (4 * D + 4) + 4 * S * D),
+        ("broadcast (E)", bc, N * 4 + 12 * S + N * 12),
+    ):
+        ms = time_it(fn)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "algorithmic_bytes": int(nbytes), "achieved": gbs, "peak": peak, "unit": "GB/s",
+                     "frac": gbs / peak, "peak_source": peak_src}
+    return out
+
+
+def run_gpu(args):
+    rank, world, local = dist_env()
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from gapro_b200 import _lib
+    from gapro_b200.engine import get_engine
+    from gapro_b200.gen_ps import to_scene_inputs
+    lib = _lib.load()
+    eng = get_engine(dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    inps = make_inputs(rank, args.scenes, args.workload)
+    scenes = [to_scene_inputs(inp, dev, noise_seed=rank * 1000 + i) for i, inp in enumerate(inps)]
+    kw = dict(thresh_spp_occu=0.999, training_iter=50)      # gen_ps.py:106-110
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = lambda: flush_buf.zero_()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    for _ in range(args.warmup):
+        flush()
+        eng.run(scenes, **kw)
+    launches_per_step = eng.last_stats["launches"]
+
+    # ---- device-resident timing (value) ---------------------------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    hist = None
+    for _ in range(args.steps):
+        flush()
+        outs = eng.run(scenes, **kw)
+    # the one collective of the job: gather of label metadata (per-rank semantic histogram)
+    sem_all = torch.cat([o[0] for o in outs]).long()
+    hist = torch.bincount(torch.where(sem_all < 0, 19, sem_all), minlength=20)
+    if world > 1:
+        gathered = [torch.empty_like(hist) for _ in range(world)]
+        dist.all_gather(gathered, hist)
+        hist = torch.stack(gathered).sum(0)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = world * args.scenes / (ms_step * 1e-3)
+    stats = dict(eng.last_stats)
+
+    # ---- end to end: pinned host inputs -> device -> hot path -> host ----------------------------
+    pinned = []
+    h2d = 0
+    for inp in inps:
+        d = {}
+        for k, dt in (("xyz", torch.float64), ("mask_feats", torch.float32), ("spp", torch.int64),
+                      ("instance_cls", torch.int64), ("instance_box", torch.float32),
+                      ("instance_box_volume", torch.float32), ("wall_box", torch.float32), ("wall_volume", torch.float32)):
+            t = torch.from_numpy(np.ascontiguousarray(inp[k])).to(dt).pin_memory()
+            d[k] = t
+            h2d += t.numel() * t.element_size()
+        pinned.append(d)
+    from gapro_b200.engine import SceneInputs
+
+    def e2e_step():
+        sc = []
+        for i, d in enumerate(pinned):
+            g = {k: v.to(dev, non_blocking=True) for k, v in d.items()}
+            sc.append(SceneInputs(g["xyz"], g["mask_feats"], g["spp"], g["instance_cls"], g["instance_box"],
+                                  g["instance_box_volume"], g["wall_box"], g["wall_volume"], noise_seed=rank * 1000 + i))
+        res = eng.run(sc, **kw)
+        host = [[t.to("cpu", non_blocking=True) for t in r] for r in res]
+        return host
+
+    flush()
+    host = e2e_step()
+    torch.cuda.synchronize(dev)
+    d2h = sum(t.numel() * t.element_size() for r in host for t in r)
+    barrier()
+    e0.record()
+    t_wall = time.perf_counter()
+    for _ in range(args.steps):
+        flush()
+        e2e_step()
+    e1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), t_wall * 1e3)) / args.steps
+    e2e_val = world * args.scenes / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (profiled step, outside the timed regions) ---------------
+    import ctypes
+    lib.gapro_gp_set_profiling(1)
+    flush()
+    eng.run(scenes, keep=True, **kw)
+    n_slots = 17
+    ms = (ctypes.c_double * n_slots)()
+    fa = (ctypes.c_double * n_slots)()
+    fe = (ctypes.c_double * n_slots)()
+    _lib.check(lib.gapro_gp_get_profile(ms, fa, fe, n_slots), "gapro_gp_get_profile")
+    lib.gapro_gp_set_profiling(0)
+    names = lib.gapro_gp_phase_names().decode().split(",")
+    phases = {n: {"ms": ms[i], "alg_gflop": fa[i] / 1e9, "exe_gflop": fe[i] / 1e9} for i, n in enumerate(names)}
+    gp_ms = sum(ms)
+    gemm_names = ["A", "B", "GA", "GT", "GC", "GL", "SP", "Y", "GK"]
+    top = max(gemm_names, key=lambda n: phases[n]["ms"])
+    scratch = torch.zeros(8, dtype=torch.float64, device=dev)
+    peak_dmma = ctypes.c_double()
+    peak_dfma = ctypes.c_double()
+    _lib.check(lib.gapro_fp64_peak(1, 20000, ctypes.byref(peak_dmma), scratch.data_ptr(), stream), "fp64 peak")
+    _lib.check(lib.gapro_fp64_peak(0, 20000, ctypes.byref(peak_dfma), scratch.data_ptr(), stream), "fp64 peak")
+    peak = max(peak_dmma.value, peak_dfma.value)
+    iters = 50
+    n_launch_top = iters       # one launch of this phase per training step (+ none in predict for most)
+    ach = phases[top]["alg_gflop"] / 1e3 / (phases[top]["ms"] * 1e-3)
+    fam_ms = sum(phases[n]["ms"] for n in gemm_names)
+    fam_alg = sum(phases[n]["alg_gflop"] for n in gemm_names) / 1e3
+    fam_exe = sum(phases[n]["exe_gflop"] for n in gemm_names) / 1e3
+    roofline = {
+        "bound": "tensor", "kernel": f"k_gemm<{top}> (FP64 DMMA tile kernel)", "achieved": ach, "peak": peak,
+        "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+        "peak_source": "in-repo FP64 microbenchmark gapro_fp64_peak (DMMA %.1f / DFMA %.1f TFLOP/s); "
+                       "MEASURED_PEAKS.json has no FP64 figure" % (peak_dmma.value, peak_dfma.value),
+        "avg_launch_ms": phases[top]["ms"] / n_launch_top, "share_of_step": phases[top]["ms"] / (ms_step),
+        "gemm_family": {"ms": fam_ms, "share_of_step": fam_ms / ms_step, "achieved_alg": fam_alg / (fam_ms * 1e-3),
+                        "achieved_issued": fam_exe / (fam_ms * 1e-3), "frac_alg": fam_alg / (fam_ms * 1e-3) / peak,
+                        "frac_issued": fam_exe / (fam_ms * 1e-3) / peak},
+        "gp_stage_ms": gp_ms, "phases_ms": {n: round(phases[n]["ms"], 3) for n in names},
+    }
+    stages = stage_rooflines(eng, lib, stream, flush)
+
+    # ---- CPU baseline (bounded sample) -------------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        n_workers = len(os.sched_getaffinity(0))
+        with mp.get_context("fork").Pool(n_workers, initializer=_warm_worker) as pool:
+            sec, desc = cpu_scene_time(inps[0], 20.0, pool, n_workers)
+        cpu = {"value": 1.0 / sec, "unit": "scenes/s", "cores": n_workers, "kind": "port", "sample": desc}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD % args.scenes, "scenes_per_gpu_per_step": args.scenes,
+                   "points_per_step_per_gpu": stats["n_points"], "superpoints": stats["n_spp"],
+                   "gp_regions_per_step_per_gpu": stats["n_regions"], "sum_M": stats["sum_m"],
+                   "gp_iters": 50, "l2": "256 MiB buffer written between steps (flush)",
+                   "label_histogram_points": int(hist.sum().item())},
+        "gp_regions_per_s": world * stats["n_regions"] / (ms_step * 1e-3),
+        "e2e": {"value": e2e_val, "unit": "scenes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clocks, "roofline": roofline, "stage_rooflines": stages, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes", type=int, default=8, help="scenes per GPU per step")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c1_deep", "c4", "c5", "small", "tiny"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                             "(use --impl reference for the CPU arm)")
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -861,6 +861,59 @@ struct ChunkTables {
     int nbmax;
 };
 
+
+// ---- opt-in per-phase profiling with CUDA events on the launching stream ------------------
+constexpr int PROF_PREDICT = PH_COUNT, PROF_SETUP = PH_COUNT + 1, PROF_SLOTS = PH_COUNT + 2;
+struct ProfSpan {
+    int slot;
+    cudaEvent_t a, b;
+};
+struct ProfState {
+    bool on = false;
+    std::vector<ProfSpan> spans;
+    double flops_alg[PROF_SLOTS] = {0};   // algorithmic flops (unpadded sizes, FMA = 2)
+    double flops_exe[PROF_SLOTS] = {0};   // flops actually issued by the tile kernels (padding, whole tiles)
+    int64_t launches[PROF_SLOTS] = {0};
+};
+thread_local ProfState g_prof;
+
+void prof_begin(int slot, cudaStream_t st) {
+    if (!g_prof.on) return;
+    ProfSpan sp;
+    sp.slot = slot;
+    cudaEventCreate(&sp.a);
+    cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, st);
+    g_prof.spans.push_back(sp);
+}
+void prof_end(cudaStream_t st) {
+    if (!g_prof.on) return;
+    cudaEventRecord(g_prof.spans.back().b, st);
+}
+
+// flops of one training step of one region, per phase
+void prof_account_train(const Region& r, int steps) {
+    if (!g_prof.on) return;
+    const double M = r.M, Mp = r.Mp, m3 = M * M * M, nb = r.nb, t3 = 2.0 * 64 * 64 * 64;
+    const double tri = nb * (nb + 1) / 2;               // lower tiles
+    const double kfull_tri = t3 * nb * tri;             // triangular operand x full: sum_ti (ti+1) * nb tiles
+    auto add = [&](int ph, double alg, double exe) {
+        g_prof.flops_alg[ph] += steps * alg;
+        g_prof.flops_exe[ph] += steps * exe;
+    };
+    add(PH_CHOL, 2.0 * m3 / 3.0, t3 * (nb * (nb + 1) * (2 * nb + 1) / 6.0 + nb * (nb - 1) / 2.0 * 2 + nb * nb * nb / 3.0));
+    add(PH_A, m3, kfull_tri);
+    add(PH_B, m3, kfull_tri);
+    add(PH_GA, m3, kfull_tri);
+    add(PH_GT, m3, t3 * tri * nb);
+    add(PH_GC, m3, kfull_tri);
+    add(PH_GL, m3, t3 * tri * nb);
+    add(PH_SP, m3 / 3.0, t3 * nb * (nb + 1) * (nb + 2) / 6.0);
+    add(PH_Y, m3, kfull_tri);
+    add(PH_GK, m3, kfull_tri);
+    (void)Mp;
+}
+
 struct Driver {
     cudaStream_t stream;
     int D;
@@ -929,8 +982,11 @@ struct Driver {
         const GpParams p = params(step, 0);
         int ph = 0;
 #define PHASE(X)                     \
-    if (ph++ >= stop_phase) return;  \
-    X;
+    if (ph >= stop_phase) return;    \
+    prof_begin(ph, stream);          \
+    X;                               \
+    prof_end(stream);                \
+    ++ph;
         PHASE(build(p))
         PHASE(cholesky(p))
         PHASE(gemm<PH_A>(tb.full, tb.n_full, p))
@@ -951,6 +1007,7 @@ struct Driver {
 
     void predict() {
         const GpParams p = params(0, 1);
+        prof_begin(PROF_PREDICT, stream);
         build(p);
         cholesky(p);
         gemm<PH_A>(tb.wide, tb.n_wide, p);
@@ -959,6 +1016,7 @@ struct Driver {
             k_colstats<<<tb.n_rowsp, 256, 0, stream>>>(tb.regs, tb.rowsp, p, ws, po);
             ++g_launches;
         }
+        prof_end(stream);
     }
 };
 
@@ -1098,12 +1156,15 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
         drv.ws = (double*)ws;
         drv.n_regs = (int)chunk.size();
         drv.po = po;
+        prof_begin(PROF_SETUP, stream);
         GAPRO_CUDA_TRY(cudaMemsetAsync(ws, 0, doubles * 8, stream));
         int rc = setup_chunk(chunk, (char*)ws + doubles * 8, stream, drv.tb);
         if (rc != GAPRO_OK) return rc;
         k_region_init<<<drv.n_regs, 256, 0, stream>>>(drv.tb.regs, D, feats_spp, train_idx, test_idx, init_noise,
                                                       drv.ws);
         ++g_launches;
+        prof_end(stream);
+        for (const Region& r : chunk) prof_account_train(r, iters);
         for (int it = 1; it <= iters; ++it) drv.train_step(it, PH_COUNT);
         if (stop_phase > 0) drv.train_step(iters + 1, stop_phase);
         if (do_predict) drv.predict();
@@ -1138,6 +1199,95 @@ extern "C" int gapro_gp_fit_batch(const float* feats_spp, int32_t D, int32_t n_r
     PredictOut po{out_prob, out_conf, out_mu, out_var, out_label, out_mu64, out_var64, status};
     return run_regions(feats_spp, D, all, train_idx, test_idx, init_noise, iters, 0, lr, jitter_zz, jitter_xx, po, ws,
                        ws_bytes, true, stream);
+}
+
+
+// ---- profiling API ---------------------------------------------------------------------------
+extern "C" int gapro_gp_set_profiling(int enable) {
+    for (ProfSpan& sp : g_prof.spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    g_prof = ProfState();
+    g_prof.on = enable != 0;
+    return GAPRO_OK;
+}
+
+extern "C" const char* gapro_gp_phase_names(void) {
+    return "build,chol,A,B,colstats,GA,GT,GM,GC,GL,SP,Y,GK,kgrad,adam,predict,setup";
+}
+
+// ms / flops per phase slot accumulated since gapro_gp_set_profiling(1).  SYNCHRONISES on the events.
+extern "C" int gapro_gp_get_profile(double* ms, double* flops_alg, double* flops_exe, int32_t cap) {
+    GAPRO_REQUIRE(ms && flops_alg && flops_exe && cap >= PROF_SLOTS, "gapro_gp_get_profile: need %d slots", PROF_SLOTS);
+    for (int i = 0; i < PROF_SLOTS; ++i) {
+        ms[i] = 0.0;
+        flops_alg[i] = g_prof.flops_alg[i];
+        flops_exe[i] = g_prof.flops_exe[i];
+    }
+    for (ProfSpan& sp : g_prof.spans) {
+        GAPRO_CUDA_TRY(cudaEventSynchronize(sp.b));
+        float t = 0.f;
+        GAPRO_CUDA_TRY(cudaEventElapsedTime(&t, sp.a, sp.b));
+        ms[sp.slot] += t;
+    }
+    return PROF_SLOTS;
+}
+
+// ---- FP64 pipe peak microbenchmark (the roofline denominator for the GP kernels) -------------------
+namespace {
+template <bool DMMA>
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
+    double acc[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (DMMA) {
+                dmma(acc[j][0], acc[j][1], a, b);
+            } else {
+                acc[j][0] = fma(a, b, acc[j][0]);
+                acc[j][1] = fma(b, a, acc[j][1]);
+            }
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += acc[j][0] + acc[j][1];
+    if (s == 12345.678) out[0] = s;
+}
+}  // namespace
+
+// Returns the sustained FP64 rate in TFLOP/s of a register-resident DMMA (use_dmma=1) or DFMA loop.
+extern "C" int gapro_fp64_peak(int use_dmma, int iters, double* tflops, double* scratch_dev, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GAPRO_REQUIRE(tflops && scratch_dev && iters > 0, "gapro_fp64_peak: bad arguments");
+    int dev = 0, sms = 0;
+    GAPRO_CUDA_TRY(cudaGetDevice(&dev));
+    GAPRO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 4, threads = 256;
+    cudaEvent_t a, b;
+    GAPRO_CUDA_TRY(cudaEventCreate(&a));
+    GAPRO_CUDA_TRY(cudaEventCreate(&b));
+    for (int rep = 0; rep < 2; ++rep) {   // first pass warms up
+        GAPRO_CUDA_TRY(cudaEventRecord(a, stream));
+        if (use_dmma)
+            k_fp64_peak<true><<<blocks, threads, 0, stream>>>(scratch_dev, iters);
+        else
+            k_fp64_peak<false><<<blocks, threads, 0, stream>>>(scratch_dev, iters);
+        GAPRO_CUDA_TRY(cudaEventRecord(b, stream));
+        GAPRO_CUDA_TRY(cudaEventSynchronize(b));
+    }
+    float ms = 0.f;
+    GAPRO_CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    // DMMA m8n8k4: 256 FMA per warp instruction; DFMA: 2 per thread per j
+    const double fma_per_block_iter = use_dmma ? (threads / 32) * 8.0 * 256.0 : threads * 8.0 * 2.0;
+    *tflops = 2.0 * fma_per_block_iter * blocks * (double)iters / (ms * 1e-3) / 1e12;
+    return GAPRO_OK;
 }
 
 extern "C" const char* gapro_gp_debug_layout_names(void) {

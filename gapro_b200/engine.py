@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, plan
 
 MARGIN = 0.005      # /root/reference/gapro/gen_ps_utils.py:350
 
@@ -87,7 +87,7 @@ class GaproEngine:
     # ------------------------------------------------------------------ main entry
     def run(self, scenes: Sequence[SceneInputs], instance_classes=18, ground_h=0.1, training_iter=50,
             thresh_spp_occu=0.8, jitter_zz=1e-4, jitter_xx=1e-4, lr=0.1, debug: bool = False,
-            want_cnt_in: bool = False):
+            want_cnt_in: bool = False, keep: bool = False):
         """Returns a list of (sem[N] i32, inst[N] i32, prob[N] f32, mu[S] f32, var[S] f32) device
         tensors, one tuple per scene — the return of gen_pseudo_label_gaussian_process
         (/root/reference/gapro/gen_ps_utils.py:482) — plus a BatchDebug when debug=True."""
@@ -185,57 +185,13 @@ class GaproEngine:
         boxes_h = boxes.cpu().numpy()
         excl_h = excl_cnt.cpu().numpy()
         inter_h = inter_cnt.cpu().numpy()
-        ev_scene, ev_kind, ev_b1, ev_b2 = [], [], [], []
-        ev_off = np.zeros(ns + 1, dtype=np.int32)
-        for i in range(ns):
-            b0, B = int(box_off[i]), int(n_box[i])
-            cap = B * B + 1
-            k_ = np.empty(cap, dtype=np.int32)
-            b1_ = np.empty(cap, dtype=np.int32)
-            b2_ = np.empty(cap, dtype=np.int32)
-            bx = np.ascontiguousarray(boxes_h[b0:b0 + B])
-            ex = np.ascontiguousarray(excl_h[b0:b0 + B])
-            ic = np.ascontiguousarray(inter_h[i])
-            n_ev = _lib.check(lib.gapro_enumerate_events(bx.ctypes.data, B, ex.ctypes.data, ic.ctypes.data, stride,
-                                                         k_.ctypes.data, b1_.ctypes.data, b2_.ctypes.data, cap),
-                              "gapro_enumerate_events")
-            ev_scene.append(np.full(n_ev, i, dtype=np.int32))
-            ev_kind.append(k_[:n_ev])
-            ev_b1.append(b1_[:n_ev])
-            ev_b2.append(b2_[:n_ev])
-            ev_off[i + 1] = ev_off[i] + n_ev
-        ev_scene = np.concatenate(ev_scene)
-        ev_kind = np.concatenate(ev_kind)
-        ev_b1 = np.concatenate(ev_b1)
-        ev_b2 = np.concatenate(ev_b2)
-        n_ev = len(ev_kind)
-        is_gp = ev_kind == _lib.EV_GP
-        gp_ev = np.flatnonzero(is_gp)
-        nest_ev = np.flatnonzero(~is_gp)
-        R = len(gp_ev)
-
-        # index lists: [GP intersections | nest intersections | training rows (b1 excl ++ b2 excl)]
-        inter_len = (inter_h[ev_scene, np.minimum(ev_b1, ev_b2), np.maximum(ev_b1, ev_b2)].astype(np.int64)
-                     if n_ev else np.zeros(0, np.int64))
-        ev_list_off = np.zeros(n_ev, dtype=np.int64)
-        order = np.concatenate([gp_ev, nest_ev])
-        offs = np.concatenate([[0], np.cumsum(inter_len[order])])
-        ev_list_off[order] = offs[:-1]
-        n_inter_total = int(offs[-1])
-        n_test_total = int(inter_len[gp_ev].sum())
-        test_off = np.zeros(R + 1, dtype=np.int32)
-        test_off[1:] = np.cumsum(inter_len[gp_ev])
-        gb0 = box_off[ev_scene[gp_ev]] if R else np.zeros(0, np.int32)
-        m1 = excl_h[gb0 + ev_b1[gp_ev]].astype(np.int64) if R else np.zeros(0, np.int64)
-        m2 = excl_h[gb0 + ev_b2[gp_ev]].astype(np.int64) if R else np.zeros(0, np.int64)
-        train_off = np.zeros(R + 1, dtype=np.int32)
-        train_off[1:] = np.cumsum(m1 + m2)
-        n_train_total = int(train_off[-1])
-        L_scene = np.concatenate([ev_scene, ev_scene[gp_ev], ev_scene[gp_ev]]).astype(np.int32)
-        L_b1 = np.concatenate([ev_b1, ev_b1[gp_ev], ev_b2[gp_ev]]).astype(np.int32)
-        L_b2 = np.concatenate([ev_b2, np.full(2 * R, -1)]).astype(np.int32)
-        L_off = np.concatenate([ev_list_off, n_inter_total + train_off[:-1],
-                                n_inter_total + train_off[:-1] + m1]).astype(np.int32)
+        ev = plan.enumerate_events(boxes_h, excl_h, inter_h, box_off, stride)
+        pl = plan.plan_lists(ev, box_off, excl_h, inter_h)
+        ev_off, ev_scene, ev_kind, ev_b1, ev_b2 = ev["ev_off"], ev["ev_scene"], ev["ev_kind"], ev["ev_b1"], ev["ev_b2"]
+        n_ev, R, gp_ev, inter_len = pl["n_events"], pl["n_regions"], pl["gp_ev"], pl["inter_len"]
+        ev_list_off, n_inter_total, n_test_total = pl["ev_list_off"], pl["n_inter_total"], pl["n_test_total"]
+        n_train_total, test_off, train_off, m1, m2 = pl["n_train_total"], pl["test_off"], pl["train_off"], pl["m1"], pl["m2"]
+        L_scene, L_b1, L_b2, L_off = pl["list_scene"], pl["list_b1"], pl["list_b2"], pl["list_off"]
         n_lists = len(L_scene)
         lists_idx = torch.empty(max(n_inter_total + n_train_total, 1), dtype=torch.int32, device=dev)
         if n_lists:
@@ -287,8 +243,7 @@ class GaproEngine:
                 raise _lib.GaproError("NanError: non-finite GP posterior")
 
         # ---- S0 + M + D + labels, then E ------------------------------------------------------
-        ev_gp_off = np.full(n_ev, -1, dtype=np.int32)
-        ev_gp_off[gp_ev] = test_off[:-1]
+        ev_gp_off = pl["ev_gp_off"]
         sem_spp = torch.empty(St, dtype=torch.int32, device=dev)
         inst_spp = torch.empty(St, dtype=torch.int32, device=dev)
         prob_spp = torch.empty(St, dtype=torch.float32, device=dev)
@@ -314,6 +269,12 @@ class GaproEngine:
                                               stream), "gapro_broadcast_labels")
         n_launch += 2
 
+        if keep:
+            self.last = dict(xyz=xyz, feats=feats, perm=perm, seg_off=seg_off, spp_gid=spp_gid, spp_off_dev=spp_off_dev,
+                             box_off_dev=box_off_dev, boxes=boxes, occ_bits=occ_bits, n_bbs=n_bbs, excl_cnt=excl_cnt,
+                             inter_cnt=inter_cnt, feats_spp=feats_spp, sem_spp=sem_spp, inst_spp=inst_spp,
+                             prob_spp=prob_spp, sem=sem, inst=inst, prob=prob, ns=ns, St=St, Bt=Bt, N=N, D=D,
+                             words=words, thresh=float(np.float32(thresh_spp_occu)))
         out = []
         for i in range(ns):
             p0, p1, s0, s1 = int(pt_off[i]), int(pt_off[i + 1]), int(spp_off[i]), int(spp_off[i + 1])

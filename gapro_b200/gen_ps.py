@@ -17,6 +17,7 @@ import argparse
 import os
 import os.path as osp
 import time
+import zlib
 from glob import glob
 
 import numpy as np
@@ -24,6 +25,7 @@ import torch
 
 from .engine import SceneInputs
 from .gen_ps_utils import gen_pseudo_labels_batch, getInstanceInfo
+from .sharding import gather_records, shard_scenes
 
 DATA_ROOT = "dataset/scannetv2"
 
@@ -135,7 +137,7 @@ def main(argv=None):
         scan = osp.basename(fn)[:12]
         if not osp.exists(osp.join(args.save_folder, scan + ".pth")):   # resume rule, gen_ps.py:39-41
             todo.append((fn, scan))
-    todo = todo[rank::world]
+    todo = shard_scenes(todo, rank, world)
 
     from .eval_ps_labels import get_miou_scene
     from .scannet_planes import get_wall_boxes
@@ -150,7 +152,7 @@ def main(argv=None):
             A = read_axis_align_matrix(osp.join(DATA_ROOT, "scans_transform", scan, scan + ".txt"))
             _, wall_box, wall_vol = get_wall_boxes(scan)
             inp = prepare_inputs(xyz, rgb, sem, inst, spp, A, wall_box, wall_vol, deep)
-            seed = None if args.seed is None else hash((args.seed, scan)) & 0x7fffffff
+            seed = None if args.seed is None else (zlib.crc32(scan.encode()) ^ args.seed) & 0x7fffffff
             scenes.append(to_scene_inputs(inp, device, noise_seed=seed))
             gts.append((sem, inst))
         results = gen_pseudo_labels_batch(scenes, instance_classes=18, ground_h=0.1, training_iter=50,
@@ -178,10 +180,10 @@ def main(argv=None):
             print("Mean instance iou of pseudo labels", torch.mean(local_iou.float()).item())
     if world > 1:
         import torch.distributed as dist
-        counts = torch.tensor([len(meta), sum(m[1] for m in meta)], dtype=torch.int64, device=device)
-        dist.all_reduce(counts)       # the one collective: label metadata over NCCL
+        records = gather_records(meta, world)       # the one collective: label metadata
         if rank == 0:
-            print(f"{int(counts[0])} scenes / {int(counts[1])} points labelled on {world} GPUs in {time.time() - t0:.1f}s")
+            print(f"{len(records)} scenes / {sum(m[1] for m in records)} points labelled on {world} GPUs "
+                  f"in {time.time() - t0:.1f}s")
         dist.destroy_process_group()
     if rank == 0:
         print("Finish")

@@ -26,12 +26,14 @@ def _plane_normal(q):
     AtA = A.T @ A
     if np.linalg.det(AtA) > 1e-10:
         fit = np.linalg.inv(AtA) @ (A.T @ q[:, 2])
-        n = np.array([fit[0] / fit[2], fit[1] / fit[2], -1.0 / fit[2]])
+        with np.errstate(divide="ignore", invalid="ignore"):     # plane through the origin: NaN, as in the reference
+            n = np.array([fit[0] / fit[2], fit[1] / fit[2], -1.0 / fit[2]])
     else:
         A2 = A[:, :2]
         fit = np.linalg.inv(A2.T @ A2) @ (A2.T @ -np.ones(4))
         n = np.array([fit[0], fit[1], 0.0])
-    return n / np.linalg.norm(n)
+    with np.errstate(invalid="ignore"):
+        return n / np.linalg.norm(n)
 
 
 def quad_to_box(q, normal):
@@ -67,7 +69,7 @@ def wall_boxes_from_planes(plane_dict, axis_align_matrix):
         if not _coplanar(q):
             continue
         n = _plane_normal(q)
-        if abs(n[2]) >= 0.2:          # vertical planes only (:218-220)
+        if not abs(n[2]) < 0.2:       # vertical planes only (:218-220); a NaN normal is dropped too
             continue
         boxes.append(quad_to_box(q, n))
     del room_centre

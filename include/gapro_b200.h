@@ -192,6 +192,19 @@ int gapro_gp_fit_batch(const float* feats_spp, int32_t D, int32_t n_regions, con
 /* number of kernel launches the last gapro_gp_fit_batch call on this thread enqueued */
 int64_t gapro_gp_last_launch_count(void);
 
+/* Opt-in profiling of gapro_gp_fit_batch (thread-local): CUDA events are recorded on the launching
+ * stream around every phase; gapro_gp_get_profile SYNCHRONISES on them and returns, per phase slot
+ * (names: gapro_gp_phase_names(), comma separated), the elapsed milliseconds, the algorithmic flops
+ * (unpadded sizes, FMA = 2) and the flops the tile kernels issued. */
+int gapro_gp_set_profiling(int enable);
+const char* gapro_gp_phase_names(void);
+int gapro_gp_get_profile(double* ms, double* flops_alg, double* flops_exe, int32_t cap);
+
+/* FP64 pipe microbenchmark: sustained TFLOP/s of a register-resident DMMA (use_dmma=1) or DFMA
+ * (use_dmma=0) loop on the current device - the measured roofline denominator of the GP kernels
+ * (MEASURED_PEAKS.json has no FP64 figure).  scratch_dev: dev double[1].  SYNCHRONISES. */
+int gapro_fp64_peak(int use_dmma, int iters, double* tflops, double* scratch_dev, void* stream);
+
 /* Debug/test hook: run ONE region for `iters` full steps plus the first
  * `stop_phase` phases of the next step, no prediction, and leave the workspace
  * as is.  layout receives the offsets (in doubles) of the region's buffers in
