@@ -15,6 +15,7 @@
 // All O(M^3) products run on the FP64 tensor pipe (mma.sync m8n8k4 f64, "DMMA") from shared
 // memory tiles filled by cp.async double buffering.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -25,9 +26,8 @@ namespace {
 
 constexpr int TB = 64;            // tile edge; every matrix dimension is padded to a multiple of it
 constexpr int BK = 16;            // k-chunk staged per pipeline stage
-constexpr int LDK = BK + 4;       // smem row stride of a k-contiguous operand tile  [64][LDK]
-constexpr int LDM = TB + 4;       // smem row stride of an m/n-contiguous operand tile [BK][LDM]
-constexpr int STAGE = TB * LDK;   // doubles per operand stage (>= BK*LDM)
+constexpr int LDK = BK + 2;       // smem row stride of a k-contiguous operand tile  [64][LDK]
+constexpr int STAGE = TB * LDK;   // doubles per operand stage (>= BK*TB of the swizzled m/n-contiguous tile)
 constexpr int GEMM_THREADS = 128;
 constexpr int N_GH = 20;
 constexpr double MIN_VARIANCE = 1e-6;
@@ -124,10 +124,12 @@ __device__ __forceinline__ void adam_update(double& p, double& m, double& v, dou
 // ---------------------------------------------------------------------------------------------
 // 64x64xK tile product on the FP64 tensor pipe
 // ---------------------------------------------------------------------------------------------
+constexpr int NSTAGE = 3;
 struct GemmSmem {
-    double a[2][STAGE];
-    double b[2][STAGE];
+    double a[NSTAGE][STAGE];
+    double b[NSTAGE][STAGE];
 };
+constexpr int GEMM_SMEM = (int)sizeof(GemmSmem);
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -143,8 +145,19 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// Operand tile: 64 rows (m or n) x 16 k.  KC = true: element(r,k) = g[r*ld + k] (k contiguous in
-// global and in smem, [64][LDK]); KC = false: element(r,k) = g[k*ld + r] (r contiguous, [16][LDM]).
+// Operand tile: 64 rows (m or n) x 16 k, staged so that every fragment load is a conflict-free
+// 128-bit shared load.
+//   KC = true : element(r,k) = g[r*ld + k]; smem [64][LDK] (k contiguous, rows padded to 18 doubles)
+//   KC = false: element(r,k) = g[k*ld + r]; smem [16][64]  (r contiguous, 16-byte units XOR-swizzled
+//               with swz(k) so that the four k-rows a quarter-warp touches fall into distinct banks)
+// Fragment <-> matrix maps (the k order inside a chunk is free as long as A and B agree):
+//   k of MMA step kk for lane (gid, tig): 4*tig + kk
+//   row of sub-tile i for lane gid:       KC ? 8*i + gid : 4*gid + i
+__device__ __forceinline__ int swz(int k) { return ((k >> 2) & 1) | (((k >> 3) & 1) << 2); }
+
+template <bool KC>
+__device__ __forceinline__ int frag_row(int i, int g) { return KC ? 8 * i + g : 4 * g + i; }
+
 template <bool KC>
 __device__ __forceinline__ void load_stage(double* s, const double* g, int ld, int k) {
     const int t = threadIdx.x;
@@ -155,78 +168,118 @@ __device__ __forceinline__ void load_stage(double* s, const double* g, int ld, i
 #pragma unroll
         for (int q = 0; q < 4; ++q) cp_async16(dst + 2 * q, src + 2 * q);
     } else {
-        const int kr = t >> 3, c = (t & 7) * 8;
-        const double* src = g + (size_t)(k + kr) * ld + c;
-        double* dst = s + kr * LDM + c;
+        const int kr = t >> 3, u = (t & 7) * 4;
+        const double* src = g + (size_t)(k + kr) * ld + 2 * u;
+        double* dst = s + kr * TB;
+        const int x = swz(kr);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cp_async16(dst + 2 * q, src + 2 * q);
+        for (int q = 0; q < 4; ++q) cp_async16(dst + 2 * ((u + q) ^ x), src + 2 * q);
     }
 }
 
-// acc[i][j][e]: row = wm*32 + i*8 + gid, col = wn*32 + j*8 + 2*tig + e
+// two MMA steps (kk = 2*h, 2*h+1) worth of fragments of one operand: f[i][0..1]
+template <bool KC>
+__device__ __forceinline__ void load_frags(double (&f)[4][2], const double* s, int w32, int gid, int tig, int h) {
+    if (KC) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 v = *reinterpret_cast<const double2*>(s + (w32 + 8 * i + gid) * LDK + 4 * tig + 2 * h);
+            f[i][0] = v.x;
+            f[i][1] = v.y;
+        }
+    } else {
+        const int u0 = (w32 >> 1) + 2 * gid, x = swz(4 * tig);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double* row = s + (4 * tig + 2 * h + e) * TB;
+            const double2 lo = *reinterpret_cast<const double2*>(row + 2 * (u0 ^ x));
+            const double2 hi = *reinterpret_cast<const double2*>(row + 2 * ((u0 + 1) ^ x));
+            f[0][e] = lo.x;
+            f[1][e] = lo.y;
+            f[2][e] = hi.x;
+            f[3][e] = hi.y;
+        }
+    }
+}
+
+// acc[i][j][e] holds C(row, col) with row = wm*32 + frag_row<AKC>(i, gid),
+//                                      col = wn*32 + frag_row<BKC>(j, 2*tig + e)
+// Three-stage cp.async pipeline, one __syncthreads per 16-deep chunk.
 template <bool AKC, bool BKC>
 __device__ __forceinline__ void gemm_accum(double (&acc)[4][4][2], const double* __restrict__ A, int lda,
                                            const double* __restrict__ B, int ldb, int k0, int k1,
                                            const double* __restrict__ kscale, GemmSmem& sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
-    const int wm = warp >> 1, wn = warp & 1;
+    const int wm32 = (warp >> 1) * 32, wn32 = (warp & 1) * 32;
     const int nchunk = (k1 - k0) / BK;
     if (nchunk <= 0) return;
-    load_stage<AKC>(sm.a[0], A, lda, k0);
-    load_stage<BKC>(sm.b[0], B, ldb, k0);
-    cp_async_commit();
-    for (int c = 0; c < nchunk; ++c) {
-        const int buf = c & 1;
-        if (c + 1 < nchunk) {
-            load_stage<AKC>(sm.a[buf ^ 1], A, lda, k0 + (c + 1) * BK);
-            load_stage<BKC>(sm.b[buf ^ 1], B, ldb, k0 + (c + 1) * BK);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+#pragma unroll
+    for (int s = 0; s < NSTAGE - 1; ++s) {
+        if (s < nchunk) {
+            load_stage<AKC>(sm.a[s], A, lda, k0 + s * BK);
+            load_stage<BKC>(sm.b[s], B, ldb, k0 + s * BK);
         }
-        __syncthreads();
-        const double* sa = sm.a[buf];
-        const double* sb = sm.b[buf];
+        cp_async_commit();
+    }
+    int stage = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        cp_async_wait<NSTAGE - 2>();   // chunk c has landed
+        __syncthreads();               // ... for every thread, and chunk c-1 is fully consumed
+        {
+            const int nc = c + NSTAGE - 1;
+            int ns = stage + NSTAGE - 1;
+            if (ns >= NSTAGE) ns -= NSTAGE;
+            if (nc < nchunk) {
+                load_stage<AKC>(sm.a[ns], A, lda, k0 + nc * BK);
+                load_stage<BKC>(sm.b[ns], B, ldb, k0 + nc * BK);
+            }
+            cp_async_commit();
+        }
+        const double* sa = sm.a[stage];
+        const double* sb = sm.b[stage];
 #pragma unroll
-        for (int kk = 0; kk < BK / 4; ++kk) {
-            double af[4], bf[4];
-            const int kq = kk * 4 + tig;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                af[i] = AKC ? sa[(wm * 32 + i * 8 + gid) * LDK + kq] : sa[kq * LDM + wm * 32 + i * 8 + gid];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                bf[j] = BKC ? sb[(wn * 32 + j * 8 + gid) * LDK + kq] : sb[kq * LDM + wn * 32 + j * 8 + gid];
+        for (int h = 0; h < 2; ++h) {
+            double af[4][2], bf[4][2];
+            load_frags<AKC>(af, sa, wm32, gid, tig, h);
+            load_frags<BKC>(bf, sb, wn32, gid, tig, h);
             if (kscale) {
-                const double sc = kscale[k0 + c * BK + kq];
+                const double2 sc = *reinterpret_cast<const double2*>(kscale + k0 + c * BK + 4 * tig + 2 * h);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) af[i] *= sc;
+                for (int i = 0; i < 4; ++i) {
+                    af[i][0] *= sc.x;
+                    af[i][1] *= sc.y;
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int e = 0; e < 2; ++e)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i][e], bf[j][e]);
         }
-        __syncthreads();
+        if (++stage == NSTAGE) stage = 0;
     }
+    cp_async_wait<0>();
+    __syncthreads();   // the stages may be reused (next product, or aliased scratch) right after
 }
 
-#define ACC_FOREACH(ROW0, COL0, ...)                                          \
-    {                                                                         \
-        const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;         \
-        const int gid_ = lane_ >> 2, tig_ = lane_ & 3;                        \
-        const int wm_ = warp_ >> 1, wn_ = warp_ & 1;                          \
-        _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                    \
-            _Pragma("unroll") for (int j_ = 0; j_ < 4; ++j_) {                \
-                const int row = (ROW0) + wm_ * 32 + i_ * 8 + gid_;            \
-                const int col = (COL0) + wn_ * 32 + j_ * 8 + 2 * tig_;        \
-                double& v0 = acc[i_][j_][0];                                  \
-                double& v1 = acc[i_][j_][1];                                  \
-                __VA_ARGS__                                                   \
-            }                                                                 \
-        }                                                                     \
+// Visits the accumulator as pairs of horizontally adjacent elements: v0 = C(row, col), v1 = C(row, col+1).
+#define ACC_FOREACH(AKC_, BKC_, ROW0, COL0, ...)                                                   \
+    {                                                                                              \
+        const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;                              \
+        const int gid_ = lane_ >> 2, tig_ = lane_ & 3;                                             \
+        const int wm_ = warp_ >> 1, wn_ = warp_ & 1;                                               \
+        _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                                         \
+            _Pragma("unroll") for (int p_ = 0; p_ < 4; ++p_) {                                     \
+                const int row = (ROW0) + wm_ * 32 + frag_row<AKC_>(i_, gid_);                      \
+                const int col = (COL0) + wn_ * 32 +                                                \
+                                ((BKC_) ? 8 * p_ + 2 * tig_ : 8 * tig_ + 4 * (p_ >> 1) + 2 * (p_ & 1)); \
+                double& v0 = (BKC_) ? acc[i_][p_][0] : acc[i_][2 * (p_ & 1)][p_ >> 1];             \
+                double& v1 = (BKC_) ? acc[i_][p_][1] : acc[i_][2 * (p_ & 1) + 1][p_ >> 1];         \
+                __VA_ARGS__                                                                        \
+            }                                                                                      \
+        }                                                                                          \
     }
 
 enum Phase {
@@ -237,7 +290,8 @@ enum Phase {
 template <int PH>
 __global__ void __launch_bounds__(GEMM_THREADS)
 k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams prm, double* __restrict__ ws) {
-    __shared__ GemmSmem sm;
+    extern __shared__ __align__(16) unsigned char smem_gemm[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_gemm);
     const int4 t = tiles[blockIdx.x];
     const Region R = regs[t.x];
     const int ti = t.y, tj = t.z;
@@ -255,11 +309,11 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
         gemm_accum<true, false>(acc, base + lay.Linv + (size_t)r0 * Mp, Mp, base + lay.Kzx + c0, Wp, 0, r0 + TB,
                                 nullptr, sm);
         double* out = base + lay.A;
-        ACC_FOREACH(r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
+        ACC_FOREACH(true, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
     } else if (PH == PH_B) {   // B = T^T * A, T lower: k >= i
         gemm_accum<false, false>(acc, base + lay.T + r0, Mp, base + lay.A + c0, Wp, r0, Mp, nullptr, sm);
         double* out = base + lay.Bm;
-        ACC_FOREACH(r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
+        ACC_FOREACH(false, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
     } else if (PH == PH_GA) {  // G_A = m g_mu^T + 2 (T B - A) diag(g_v)
         gemm_accum<true, false>(acc, base + lay.T + (size_t)r0 * Mp, Mp, base + lay.Bm + c0, Wp, 0, r0 + TB, nullptr,
                                 sm);
@@ -268,7 +322,7 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
         const double* gmu = base + lay.gmu;
         const double* gv = base + lay.gv;
         double* out = base + lay.GA;
-        ACC_FOREACH(r0, c0, {
+        ACC_FOREACH(true, false, r0, c0, {
             const double2 a = *reinterpret_cast<const double2*>(Am + (size_t)row * Wp + col);
             const double mi = mv[row];
             double2 o;
@@ -283,7 +337,7 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
         double* Tm = base + lay.Tm;
         double* Tv = base + lay.Tv;
         const double invN = 1.0 / (double)R.M;
-        ACC_FOREACH(r0, c0, {
+        ACC_FOREACH(true, true, r0, c0, {
             _Pragma("unroll") for (int e = 0; e < 2; ++e) {
                 const int cc = col + e;
                 if (row < R.M && cc <= row) {
@@ -301,12 +355,12 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
     } else if (PH == PH_GC) {  // G_C = Linv^T * G_A: k >= i
         gemm_accum<false, false>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, Mp, nullptr, sm);
         double* out = base + lay.GC;
-        ACC_FOREACH(r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = make_double2(v0, v1); })
+        ACC_FOREACH(false, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = make_double2(v0, v1); })
     } else if (PH == PH_GL) {  // G_L = -tril(G_C A^T)   (into the G_A buffer)
         gemm_accum<true, true>(acc, base + lay.GC + (size_t)r0 * Mp, Mp, base + lay.A + (size_t)c0 * Wp, Wp, 0, Mp,
                                nullptr, sm);
         double* out = base + lay.GA;
-        ACC_FOREACH(r0, c0, {
+        ACC_FOREACH(true, true, r0, c0, {
             double2 o;
             o.x = (col <= row) ? -v0 : 0.0;
             o.y = (col + 1 <= row) ? -v1 : 0.0;
@@ -315,7 +369,7 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
     } else if (PH == PH_SP) {  // symP = 1/2 (P + P^T), P = Phi(L^T G_L): both = 1/2 tril(L^T G_L) mirrored
         gemm_accum<false, false>(acc, base + lay.L + r0, Mp, base + lay.GA + c0, Mp, r0, Mp, nullptr, sm);
         double* out = base + lay.Bm;
-        ACC_FOREACH(r0, c0, {
+        ACC_FOREACH(false, false, r0, c0, {
             _Pragma("unroll") for (int e = 0; e < 2; ++e) {
                 const int cc = col + e;
                 const double v = 0.5 * (e ? v1 : v0);
@@ -329,11 +383,17 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
         gemm_accum<true, false>(acc, base + lay.Bm + (size_t)r0 * Wp, Wp, base + lay.Linv + c0, Mp, c0, Mp, nullptr,
                                 sm);
         double* out = base + lay.GA;
-        ACC_FOREACH(r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = make_double2(v0, v1); })
-    } else if (PH == PH_GK) {  // G_K = Linv^T * Y: k >= i   (into the B buffer)
+        ACC_FOREACH(true, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = make_double2(v0, v1); })
+    } else if (PH == PH_GK) {  // G_K = Linv^T * Y (symmetric): lower tiles, mirrored   (into the B buffer)
         gemm_accum<false, false>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, Mp, nullptr, sm);
         double* out = base + lay.Bm;
-        ACC_FOREACH(r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
+        ACC_FOREACH(false, false, r0, c0, {
+            *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1);
+            if (ti != tj) {
+                out[(size_t)col * Wp + row] = v0;
+                out[(size_t)(col + 1) * Wp + row] = v1;
+            }
+        })
     }
 }
 
@@ -400,68 +460,89 @@ k_build(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParam
 //          Linv[kb,j] = -Linv_kk sum_{k=j..kb-1} L[kb,k] Linv[k,j]              (j < kb)
 // ---------------------------------------------------------------------------------------------
 constexpr int LDS_ = TB + 1;
-constexpr int DIAG_SMEM = (int)sizeof(GemmSmem) + TB * LDS_ * (int)sizeof(double);
-static_assert(TB * LDS_ * sizeof(double) <= sizeof(GemmSmem), "inverse tile must fit in the GEMM stages");
+constexpr int DIAG_SMEM = GEMM_SMEM + TB * LDS_ * (int)sizeof(double);
+static_assert((TB * LDS_ + 3 * TB) * sizeof(double) <= sizeof(GemmSmem), "inverse tile + scratch must fit in the stages");
 
+__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+// Diagonal step.  The 64x64 factorisation and the triangular inverse are register-resident and
+// fully unrolled: thread r of warps 0-1 owns row r (then column r of the inverse); one named
+// barrier per column, pivots through rsqrt instead of sqrt + divide.
 __global__ void __launch_bounds__(GEMM_THREADS)
 k_chol_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __restrict__ ws, int32_t* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_diag[];
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_diag);
     double* sL = reinterpret_cast<double*>(smem_diag + sizeof(GemmSmem));
     double* sX = reinterpret_cast<double*>(smem_diag);   // aliases the GEMM stages (dead after the product)
+    double* colbuf = sX + TB * LDS_;                     // [2][64]
+    double* dinv = colbuf + 2 * TB;                      // [64]
     const Region R = regs[blockIdx.x];
     const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
     double* base = ws + R.base;
     const int Mp = R.Mp;
     double* Lg = base + lay.L;
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const int r0 = kb * TB;
-    gemm_accum<true, true>(acc, Lg + (size_t)r0 * Mp, Mp, Lg + (size_t)r0 * Mp, Mp, 0, r0, nullptr, sm);
-    ACC_FOREACH(0, 0, {
-        const double2 k = *reinterpret_cast<const double2*>(Lg + (size_t)(r0 + row) * Mp + r0 + col);
-        sL[row * LDS_ + col] = k.x - v0;
-        sL[row * LDS_ + col + 1] = k.y - v1;
-    })
-    __syncthreads();
-    // unblocked right-looking Cholesky of the 64x64 tile (lower)
     const int tid = threadIdx.x;
-    const int rr = tid & 63, half = tid >> 6;
-    bool bad = false;
-    for (int c = 0; c < TB; ++c) {
-        double d = sL[c * LDS_ + c];
-        if (!(d > 0.0)) {
-            bad = true;
-            d = 1.0;
-        }
-        const double piv = sqrt(d);
-        double l = 0.0;
-        if (half == 0 && rr > c) l = sL[rr * LDS_ + c] / piv;
-        __syncthreads();
-        if (half == 0) {
-            if (rr > c) sL[rr * LDS_ + c] = l;
-            if (rr == c) sL[c * LDS_ + c] = piv;
-        }
-        __syncthreads();
-        if (rr > c) {
-            const double lr = sL[rr * LDS_ + c];
-            for (int cc = c + 1 + half; cc <= rr; cc += 2) sL[rr * LDS_ + cc] -= lr * sL[cc * LDS_ + c];
-        }
-        __syncthreads();
+    {
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        gemm_accum<true, true>(acc, Lg + (size_t)r0 * Mp, Mp, Lg + (size_t)r0 * Mp, Mp, 0, r0, nullptr, sm);
+        ACC_FOREACH(true, true, 0, 0, {
+            const double2 k = *reinterpret_cast<const double2*>(Lg + (size_t)(r0 + row) * Mp + r0 + col);
+            sL[row * LDS_ + col] = k.x - v0;
+            sL[row * LDS_ + col + 1] = k.y - v1;
+        })
     }
-    if (bad && tid == 0) atomicOr(status + R.orig, GAPRO_GP_NOT_PSD);
-    // inverse of the lower-triangular tile, one column per thread
+    __syncthreads();
     if (tid < TB) {
-        const int c = tid;
-        sX[c * LDS_ + c] = 1.0 / sL[c * LDS_ + c];
-        for (int r = c + 1; r < TB; ++r) {
-            double s = 0.0;
-            for (int k = c; k < r; ++k) s += sL[r * LDS_ + k] * sX[k * LDS_ + c];
-            sX[r * LDS_ + c] = -s / sL[r * LDS_ + r];
+        const int r = tid;
+        double a[TB];
+#pragma unroll
+        for (int k = 0; k < TB; ++k) a[k] = sL[r * LDS_ + k];
+        bool bad = false;
+#pragma unroll
+        for (int c = 0; c < TB; ++c) {
+            double* col = colbuf + (c & 1) * TB;
+            col[r] = a[c];
+            bar64();
+            double piv = col[c];
+            if (!(piv > 0.0)) {
+                bad = true;
+                piv = 1.0;
+            }
+            const double rs = rsqrt(piv);
+            const double f = a[c] * (rs * rs);
+#pragma unroll
+            for (int cc = c + 1; cc < TB; ++cc) {
+                const double t = fma(-f, col[cc], a[cc]);
+                a[cc] = (cc <= r) ? t : a[cc];
+            }
+            a[c] = (r >= c) ? a[c] * rs : 0.0;
+            if (r == c) dinv[c] = rs;
         }
+        if (bad && r == 0) atomicOr(status + R.orig, GAPRO_GP_NOT_PSD);
+#pragma unroll
+        for (int k = 0; k < TB; ++k) sL[r * LDS_ + k] = a[k];
+        bar64();
+        // column r of X = L^-1 by forward substitution; entries above the diagonal come out as 0
+        double x[TB];
+#pragma unroll
+        for (int q = 0; q < TB; ++q) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < q; ++k) {
+                if (k & 1)
+                    s1 = fma(sL[q * LDS_ + k], x[k], s1);
+                else
+                    s0 = fma(sL[q * LDS_ + k], x[k], s0);
+            }
+            x[q] = (q == r) ? dinv[q] : -(s0 + s1) * dinv[q];
+        }
+#pragma unroll
+        for (int q = 0; q < TB; ++q) sX[q * LDS_ + r] = x[q];
     }
     __syncthreads();
     double* Li = base + lay.Linv;
@@ -476,7 +557,8 @@ k_chol_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __res
 __global__ void __launch_bounds__(GEMM_THREADS)
 k_chol_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, int kb, GpParams prm,
              double* __restrict__ ws, double* __restrict__ scratch) {
-    __shared__ GemmSmem sm;
+    extern __shared__ __align__(16) unsigned char smem_panel[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_panel);
     const int2 pt = ptiles[blockIdx.x];
     const Region R = regs[pt.x];
     const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
@@ -495,7 +577,7 @@ k_chol_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, i
         // L panel tile i = pt.y + 1 > kb
         const int i0 = (pt.y + 1) * TB;
         gemm_accum<true, true>(acc, Lg + (size_t)i0 * Mp, Mp, Lg + (size_t)r0 * Mp, Mp, 0, r0, nullptr, sm);
-        ACC_FOREACH(0, 0, {
+        ACC_FOREACH(true, true, 0, 0, {
             const double2 k = *reinterpret_cast<const double2*>(Lg + (size_t)(i0 + row) * Mp + r0 + col);
             *reinterpret_cast<double2*>(tmp + row * TB + col) = make_double2(k.x - v0, k.y - v1);
         })
@@ -506,14 +588,14 @@ k_chol_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, i
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
         // out[r,c] = sum_k tmp[r,k] Linv_kk[c,k]
         gemm_accum<true, true>(acc, tmp, TB, Li + (size_t)r0 * Mp + r0, Mp, 0, TB, nullptr, sm);
-        ACC_FOREACH(0, 0, {
+        ACC_FOREACH(true, true, 0, 0, {
             *reinterpret_cast<double2*>(Lg + (size_t)(i0 + row) * Mp + r0 + col) = make_double2(v0, v1);
         })
     } else {
         // Linv row tile j = pt.y < kb
         const int j0 = pt.y * TB;
         gemm_accum<true, false>(acc, Lg + (size_t)r0 * Mp, Mp, Li + j0, Mp, j0, r0, nullptr, sm);
-        ACC_FOREACH(0, 0, { *reinterpret_cast<double2*>(tmp + row * TB + col) = make_double2(v0, v1); })
+        ACC_FOREACH(true, false, 0, 0, { *reinterpret_cast<double2*>(tmp + row * TB + col) = make_double2(v0, v1); })
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -521,7 +603,7 @@ k_chol_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, i
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
         // out[r,c] = -sum_k Linv_kk[r,k] tmp[k,c]
         gemm_accum<true, false>(acc, Li + (size_t)r0 * Mp + r0, Mp, tmp, TB, 0, TB, nullptr, sm);
-        ACC_FOREACH(0, 0, {
+        ACC_FOREACH(true, false, 0, 0, {
             *reinterpret_cast<double2*>(Li + (size_t)(r0 + row) * Mp + j0 + col) = make_double2(-v0, -v1);
         })
     }
@@ -910,7 +992,7 @@ void prof_account_train(const Region& r, int steps) {
     add(PH_GL, m3, t3 * tri * nb);
     add(PH_SP, m3 / 3.0, t3 * nb * (nb + 1) * (nb + 2) / 6.0);
     add(PH_Y, m3, kfull_tri);
-    add(PH_GK, m3, kfull_tri);
+    add(PH_GK, m3 / 3.0, t3 * nb * (nb + 1) * (nb + 2) / 6.0);
     (void)Mp;
 }
 
@@ -942,7 +1024,7 @@ struct Driver {
     template <int PH>
     void gemm(const int4* tiles, int n, const GpParams& p) {
         if (n <= 0) return;
-        k_gemm<PH><<<n, GEMM_THREADS, 0, stream>>>(tb.regs, tiles, p, ws);
+        k_gemm<PH><<<n, GEMM_THREADS, GEMM_SMEM, stream>>>(tb.regs, tiles, p, ws);
         ++g_launches;
     }
 
@@ -961,7 +1043,7 @@ struct Driver {
             ++g_launches;
             const int np = tb.panel_prefix[kb];
             if (np > 0) {
-                k_chol_panel<<<np, GEMM_THREADS, 0, stream>>>(tb.regs, tb.panel, kb, p, ws, tb.scratch);
+                k_chol_panel<<<np, GEMM_THREADS, GEMM_SMEM, stream>>>(tb.regs, tb.panel, kb, p, ws, tb.scratch);
                 ++g_launches;
             }
         }
@@ -999,7 +1081,7 @@ struct Driver {
         PHASE(gemm<PH_GL>(tb.lower, tb.n_lower, p))
         PHASE(gemm<PH_SP>(tb.lower, tb.n_lower, p))
         PHASE(gemm<PH_Y>(tb.full, tb.n_full, p))
-        PHASE(gemm<PH_GK>(tb.full, tb.n_full, p))
+        PHASE(gemm<PH_GK>(tb.lower, tb.n_lower, p))
         PHASE(kgrad(p))
         PHASE((k_adam_small<<<n_regs, 256, 0, stream>>>(tb.regs, p, ws), ++g_launches))
 #undef PHASE
@@ -1115,17 +1197,70 @@ extern "C" size_t gapro_gp_min_workspace_bytes(int32_t n_regions, const int32_t*
 
 extern "C" int64_t gapro_gp_last_launch_count(void) { return g_launches; }
 
+// ---- side streams: independent region groups run concurrently so that the latency-bound
+// Cholesky sweep of one group overlaps the tile products of the others --------------------------------
+constexpr int MAX_GROUPS = 4;
+struct StreamPool {
+    cudaStream_t s[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    bool ready = false;
+};
+thread_local StreamPool g_pool;
+
+static int ensure_pool() {
+    if (g_pool.ready) return GAPRO_OK;
+    for (int i = 0; i < MAX_GROUPS; ++i) {
+        GAPRO_CUDA_TRY(cudaStreamCreateWithFlags(&g_pool.s[i], cudaStreamNonBlocking));
+        GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.join[i], cudaEventDisableTiming));
+    }
+    GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.fork, cudaEventDisableTiming));
+    g_pool.ready = true;
+    return GAPRO_OK;
+}
+
+static int n_groups_for(size_t n_regions) {
+    int g = MAX_GROUPS;
+    if (const char* e = getenv("GAPRO_GP_STREAMS")) g = atoi(e);
+    if (g < 1) g = 1;
+    if (g > MAX_GROUPS) g = MAX_GROUPS;
+    if (g_prof.on) g = 1;                       // per-phase event timing needs a single stream
+    while (g > 1 && n_regions < (size_t)4 * g) --g;
+    return g;
+}
+
+template <typename K>
+static int allow_smem(K kernel, int bytes) {
+    GAPRO_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return GAPRO_OK;
+}
+
+static int set_kernel_attributes() {
+    static bool done = false;
+    if (done) return GAPRO_OK;
+    int rc = allow_smem(k_build, 3 * TB * 64 * 8);
+    if (rc == GAPRO_OK) rc = allow_smem(k_chol_diag, DIAG_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_chol_panel, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_A>, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_B>, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GA>, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GT>, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GC>, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GL>, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_SP>, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_Y>, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GK>, GEMM_SMEM);
+    done = rc == GAPRO_OK;
+    return rc;
+}
+
 static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& all, const int32_t* train_idx,
                        const int32_t* test_idx, const float* init_noise, int32_t iters, int32_t stop_phase, double lr,
                        double jitter_zz, double jitter_xx, PredictOut po, void* ws, size_t ws_bytes, bool do_predict,
                        cudaStream_t stream) {
     GAPRO_REQUIRE(D >= 1 && D <= 64, "gp: feature dimension %d not in [1, 64]", D);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TB * 64 * 8));
-        GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_chol_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
-        attr_set = true;
-    }
+    int rc = set_kernel_attributes();
+    if (rc != GAPRO_OK) return rc;
+    const size_t group_slack = (size_t)MAX_GROUPS * 8 * 256;
     size_t pos = 0;
     while (pos < all.size()) {
         // greedy chunk: as many regions (already sorted by size) as fit in the workspace
@@ -1136,7 +1271,7 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             r.base = (long long)doubles;
             chunk.push_back(r);
             size_t nd = doubles + region_doubles(r, D);
-            if (nd * 8 + aux_bytes(chunk) > ws_bytes) {
+            if (nd * 8 + aux_bytes(chunk) + group_slack > ws_bytes) {
                 chunk.pop_back();
                 break;
             }
@@ -1147,27 +1282,51 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
                             all[pos].M, all[pos].N);
             return GAPRO_ERR_WORKSPACE;
         }
-        Driver drv;
-        drv.stream = stream;
-        drv.D = D;
-        drv.lr = lr;
-        drv.jitter_zz = jitter_zz;
-        drv.jitter_xx = jitter_xx;
-        drv.ws = (double*)ws;
-        drv.n_regs = (int)chunk.size();
-        drv.po = po;
+        const int G = n_groups_for(chunk.size());
+        if (G > 1 && (rc = ensure_pool()) != GAPRO_OK) return rc;
+        // round-robin over the size-sorted list: every group sees the same size distribution
+        std::vector<std::vector<Region>> groups(G);
+        for (size_t i = 0; i < chunk.size(); ++i) groups[i % G].push_back(chunk[i]);
+        std::vector<Driver> drv(G);
         prof_begin(PROF_SETUP, stream);
         GAPRO_CUDA_TRY(cudaMemsetAsync(ws, 0, doubles * 8, stream));
-        int rc = setup_chunk(chunk, (char*)ws + doubles * 8, stream, drv.tb);
-        if (rc != GAPRO_OK) return rc;
-        k_region_init<<<drv.n_regs, 256, 0, stream>>>(drv.tb.regs, D, feats_spp, train_idx, test_idx, init_noise,
-                                                      drv.ws);
-        ++g_launches;
+        char* aux = (char*)ws + doubles * 8;
+        for (int g = 0; g < G; ++g) {
+            Driver& d = drv[g];
+            d.stream = G > 1 ? g_pool.s[g] : stream;
+            d.D = D;
+            d.lr = lr;
+            d.jitter_zz = jitter_zz;
+            d.jitter_xx = jitter_xx;
+            d.ws = (double*)ws;
+            d.n_regs = (int)groups[g].size();
+            d.po = po;
+            rc = setup_chunk(groups[g], aux, stream, d.tb);     // uploads on the caller's stream, then syncs
+            if (rc != GAPRO_OK) return rc;
+            aux += aux_bytes(groups[g]);
+        }
+        if (G > 1) {
+            GAPRO_CUDA_TRY(cudaEventRecord(g_pool.fork, stream));
+            for (int g = 0; g < G; ++g) GAPRO_CUDA_TRY(cudaStreamWaitEvent(drv[g].stream, g_pool.fork, 0));
+        }
+        for (int g = 0; g < G; ++g) {
+            k_region_init<<<drv[g].n_regs, 256, 0, drv[g].stream>>>(drv[g].tb.regs, D, feats_spp, train_idx, test_idx,
+                                                                    init_noise, drv[g].ws);
+            ++g_launches;
+        }
         prof_end(stream);
         for (const Region& r : chunk) prof_account_train(r, iters);
-        for (int it = 1; it <= iters; ++it) drv.train_step(it, PH_COUNT);
-        if (stop_phase > 0) drv.train_step(iters + 1, stop_phase);
-        if (do_predict) drv.predict();
+        for (int it = 1; it <= iters; ++it)
+            for (int g = 0; g < G; ++g) drv[g].train_step(it, PH_COUNT);
+        if (stop_phase > 0)
+            for (int g = 0; g < G; ++g) drv[g].train_step(iters + 1, stop_phase);
+        if (do_predict)
+            for (int g = 0; g < G; ++g) drv[g].predict();
+        if (G > 1)
+            for (int g = 0; g < G; ++g) {
+                GAPRO_CUDA_TRY(cudaEventRecord(g_pool.join[g], drv[g].stream));
+                GAPRO_CUDA_TRY(cudaStreamWaitEvent(stream, g_pool.join[g], 0));
+            }
         GAPRO_KERNEL_CHECK();
         pos += chunk.size();
         if (pos < all.size()) GAPRO_CUDA_TRY(cudaStreamSynchronize(stream));   // workspace is reused
