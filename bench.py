@@ -228,15 +228,14 @@ def stage_rooflines(eng, lib, stream, flush):
         L["occ_bits"].data_ptr(), L["n_bbs"].data_ptr(), 0, L["excl_cnt"].data_ptr(), L["inter_cnt"].data_ptr(), stream), "occ")
     pool = lambda: _lib.check(lib.gapro_pool_feats(L["feats"].data_ptr(), L["perm"].data_ptr(), L["seg_off"].data_ptr(),
                                                    S, D, L["feats_spp"].data_ptr(), stream), "pool")
-    bc = lambda: _lib.check(lib.gapro_broadcast_labels(L["spp_gid"].data_ptr(), N, L["sem_spp"].data_ptr(),
-                                                       L["inst_spp"].data_ptr(), L["prob_spp"].data_ptr(),
+    bc = lambda: _lib.check(lib.gapro_broadcast_labels(L["spp_gid"].data_ptr(), N, L["packed_spp"].data_ptr(),
                                                        L["sem"].data_ptr(), L["inst"].data_ptr(), L["prob"].data_ptr(),
                                                        stream), "bcast")
     out = {}
     for name, fn, nbytes in (
         ("containment+occupancy (A+A')", occ, N * (24 + 4) + 48 * Bt + 4 * S * words + 4 * S),
         ("feature pooling (B)", pool, N * (4 * D + 4) + 4 * S * D),
-        ("broadcast (E)", bc, N * 4 + 12 * S + N * 12),
+        ("broadcast (E)", bc, N * 4 + 16 * S + N * 12),
     ):
         ms = time_it(fn)
         gbs = nbytes / (ms * 1e-3) / 1e9

@@ -43,8 +43,8 @@ _SIGNATURES = {
                                           c_double, c_double, c_double, P, c_size_t, P, c_int32, P]),
     "gapro_gp_debug_layout_names": (c_char_p, []),
     "gapro_resolve_spp": (ctypes.c_int, [P, P, c_int32, P, P, P, P, P, c_int32, c_int32, P, P, P, P, P, P, P, P,
-                                         P, P, P, P, P, P, P, P, P, P]),
-    "gapro_broadcast_labels": (ctypes.c_int, [P, c_int64, P, P, P, P, P, P, P]),
+                                         P, P, P, P, P, P, P, P, P, P, P]),
+    "gapro_broadcast_labels": (ctypes.c_int, [P, c_int64, P, P, P, P, P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

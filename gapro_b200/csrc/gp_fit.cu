@@ -208,10 +208,13 @@ __device__ __forceinline__ void load_frags(double (&f)[4][2], const double* s, i
 template <bool AKC, bool BKC>
 __device__ __forceinline__ void gemm_accum(double (&acc)[4][4][2], const double* __restrict__ A, int lda,
                                            const double* __restrict__ B, int ldb, int k0, int k1,
-                                           const double* __restrict__ kscale, GemmSmem& sm) {
+                                           const double* __restrict__ kscale, GemmSmem& sm, int mlim = TB,
+                                           int nlim = TB) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int wm32 = (warp >> 1) * 32, wn32 = (warp & 1) * 32;
+    // a warp whose 32x32 block lies entirely in the zero padding only helps with the loads
+    const bool active = wm32 < mlim && wn32 < nlim;
     const int nchunk = (k1 - k0) / BK;
     if (nchunk <= 0) return;
 #pragma unroll
@@ -240,6 +243,7 @@ __device__ __forceinline__ void gemm_accum(double (&acc)[4][4][2], const double*
         const double* sb = sm.b[stage];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            if (!active) break;
             double af[4][2], bf[4][2];
             load_frags<AKC>(af, sa, wm32, gid, tig, h);
             load_frags<BKC>(bf, sb, wn32, gid, tig, h);
@@ -304,19 +308,25 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const int r0 = ti * TB, c0 = tj * TB;
+    // padding rows/columns are exact zeros in every operand of these products: clip the contraction to
+    // the real size (rounded to the chunk) and skip warps that would only produce padding
+    const int kend = (R.M + BK - 1) / BK * BK;
+    const int ncol = prm.predict ? R.N : R.M;
+    const int mlim = (R.M + 31) / 32 * 32 - r0, nlim = (ncol + 31) / 32 * 32 - c0;
+#define KCLIP(k) ((k) < kend ? (k) : kend)
 
     if (PH == PH_A) {          // A = Linv * Kzx, Linv lower: k <= i
-        gemm_accum<true, false>(acc, base + lay.Linv + (size_t)r0 * Mp, Mp, base + lay.Kzx + c0, Wp, 0, r0 + TB,
-                                nullptr, sm);
+        gemm_accum<true, false>(acc, base + lay.Linv + (size_t)r0 * Mp, Mp, base + lay.Kzx + c0, Wp, 0, KCLIP(r0 + TB),
+                                nullptr, sm, mlim, nlim);
         double* out = base + lay.A;
         ACC_FOREACH(true, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
     } else if (PH == PH_B) {   // B = T^T * A, T lower: k >= i
-        gemm_accum<false, false>(acc, base + lay.T + r0, Mp, base + lay.A + c0, Wp, r0, Mp, nullptr, sm);
+        gemm_accum<false, false>(acc, base + lay.T + r0, Mp, base + lay.A + c0, Wp, r0, kend, nullptr, sm, mlim, nlim);
         double* out = base + lay.Bm;
         ACC_FOREACH(false, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
     } else if (PH == PH_GA) {  // G_A = m g_mu^T + 2 (T B - A) diag(g_v)
-        gemm_accum<true, false>(acc, base + lay.T + (size_t)r0 * Mp, Mp, base + lay.Bm + c0, Wp, 0, r0 + TB, nullptr,
-                                sm);
+        gemm_accum<true, false>(acc, base + lay.T + (size_t)r0 * Mp, Mp, base + lay.Bm + c0, Wp, 0, KCLIP(r0 + TB), nullptr,
+                                sm, mlim, nlim);
         const double* Am = base + lay.A;
         const double* mv = base + lay.m;
         const double* gmu = base + lay.gmu;
@@ -331,8 +341,8 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
             *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = o;
         })
     } else if (PH == PH_GT) {  // dT = tril(2 A diag(g_v) B^T + (T - diag(1/T_ii))/N), Adam on T
-        gemm_accum<true, true>(acc, base + lay.A + (size_t)r0 * Wp, Wp, base + lay.Bm + (size_t)c0 * Wp, Wp, 0, Mp,
-                               base + lay.gv, sm);
+        gemm_accum<true, true>(acc, base + lay.A + (size_t)r0 * Wp, Wp, base + lay.Bm + (size_t)c0 * Wp, Wp, 0, kend,
+                               base + lay.gv, sm, mlim, nlim);
         double* T = base + lay.T;
         double* Tm = base + lay.Tm;
         double* Tv = base + lay.Tv;
@@ -353,12 +363,12 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
             }
         })
     } else if (PH == PH_GC) {  // G_C = Linv^T * G_A: k >= i
-        gemm_accum<false, false>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, Mp, nullptr, sm);
+        gemm_accum<false, false>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, kend, nullptr, sm, mlim, nlim);
         double* out = base + lay.GC;
         ACC_FOREACH(false, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = make_double2(v0, v1); })
     } else if (PH == PH_GL) {  // G_L = -tril(G_C A^T)   (into the G_A buffer)
-        gemm_accum<true, true>(acc, base + lay.GC + (size_t)r0 * Mp, Mp, base + lay.A + (size_t)c0 * Wp, Wp, 0, Mp,
-                               nullptr, sm);
+        gemm_accum<true, true>(acc, base + lay.GC + (size_t)r0 * Mp, Mp, base + lay.A + (size_t)c0 * Wp, Wp, 0, kend,
+                               nullptr, sm, mlim, nlim);
         double* out = base + lay.GA;
         ACC_FOREACH(true, true, r0, c0, {
             double2 o;
@@ -367,7 +377,7 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
             *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = o;
         })
     } else if (PH == PH_SP) {  // symP = 1/2 (P + P^T), P = Phi(L^T G_L): both = 1/2 tril(L^T G_L) mirrored
-        gemm_accum<false, false>(acc, base + lay.L + r0, Mp, base + lay.GA + c0, Mp, r0, Mp, nullptr, sm);
+        gemm_accum<false, false>(acc, base + lay.L + r0, Mp, base + lay.GA + c0, Mp, r0, kend, nullptr, sm, mlim, nlim);
         double* out = base + lay.Bm;
         ACC_FOREACH(false, false, r0, c0, {
             _Pragma("unroll") for (int e = 0; e < 2; ++e) {
@@ -380,12 +390,12 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
             }
         })
     } else if (PH == PH_Y) {   // Y = symP * Linv: k >= j   (into the G_A buffer)
-        gemm_accum<true, false>(acc, base + lay.Bm + (size_t)r0 * Wp, Wp, base + lay.Linv + c0, Mp, c0, Mp, nullptr,
-                                sm);
+        gemm_accum<true, false>(acc, base + lay.Bm + (size_t)r0 * Wp, Wp, base + lay.Linv + c0, Mp, c0, kend, nullptr,
+                                sm, mlim, nlim);
         double* out = base + lay.GA;
         ACC_FOREACH(true, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = make_double2(v0, v1); })
     } else if (PH == PH_GK) {  // G_K = Linv^T * Y (symmetric): lower tiles, mirrored   (into the B buffer)
-        gemm_accum<false, false>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, Mp, nullptr, sm);
+        gemm_accum<false, false>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, kend, nullptr, sm, mlim, nlim);
         double* out = base + lay.Bm;
         ACC_FOREACH(false, false, r0, c0, {
             *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1);
@@ -396,6 +406,8 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
         })
     }
 }
+
+#undef KCLIP
 
 // ---------------------------------------------------------------------------------------------
 // kernel matrices: K_zz = s exp(-r2/2) + jitter I (lower tiles), K_zx = s exp(-r2/2)
@@ -468,16 +480,14 @@ __device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "me
 // Diagonal step.  The 64x64 factorisation and the triangular inverse are register-resident and
 // fully unrolled: thread r of warps 0-1 owns row r (then column r of the inverse); one named
 // barrier per column, pivots through rsqrt instead of sqrt + divide.
-__global__ void __launch_bounds__(GEMM_THREADS)
-k_chol_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __restrict__ ws, int32_t* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem_diag[];
+__device__ __forceinline__ void diag_step(const Region& R, int D, int kb, double* __restrict__ ws,
+                                          int32_t* __restrict__ status, unsigned char* smem_diag) {
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_diag);
     double* sL = reinterpret_cast<double*>(smem_diag + sizeof(GemmSmem));
     double* sX = reinterpret_cast<double*>(smem_diag);   // aliases the GEMM stages (dead after the product)
     double* colbuf = sX + TB * LDS_;                     // [2][64]
     double* dinv = colbuf + 2 * TB;                      // [64]
-    const Region R = regs[blockIdx.x];
-    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
     double* base = ws + R.base;
     const int Mp = R.Mp;
     double* Lg = base + lay.L;
@@ -491,7 +501,7 @@ k_chol_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __res
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
         gemm_accum<true, true>(acc, Lg + (size_t)r0 * Mp, Mp, Lg + (size_t)r0 * Mp, Mp, 0, r0, nullptr, sm);
         ACC_FOREACH(true, true, 0, 0, {
-            const double2 k = *reinterpret_cast<const double2*>(Lg + (size_t)(r0 + row) * Mp + r0 + col);
+            const double2 k = __ldcg(reinterpret_cast<const double2*>(Lg + (size_t)(r0 + row) * Mp + r0 + col));
             sL[row * LDS_ + col] = k.x - v0;
             sL[row * LDS_ + col + 1] = k.y - v1;
         })
@@ -555,30 +565,31 @@ k_chol_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __res
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS)
-k_chol_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, int kb, GpParams prm,
-             double* __restrict__ ws, double* __restrict__ scratch) {
-    extern __shared__ __align__(16) unsigned char smem_panel[];
-    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_panel);
-    const int2 pt = ptiles[blockIdx.x];
-    const Region R = regs[pt.x];
-    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
+k_chol_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __restrict__ ws, int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_diag[];
+    const Region R = regs[blockIdx.x];
+    diag_step(R, prm.D, kb, ws, status, smem_diag);
+}
+
+__device__ __forceinline__ void panel_tile(const Region& R, int D, int kb, int pty, double* __restrict__ ws,
+                                           double* __restrict__ tmp, GemmSmem& sm) {
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
     double* base = ws + R.base;
     const int Mp = R.Mp;
     double* Lg = base + lay.L;
     double* Li = base + lay.Linv;
-    double* tmp = scratch + (size_t)blockIdx.x * TB * TB;   // this CTA's 64x64 intermediate
     const int r0 = kb * TB;
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    if (pt.y >= kb) {
+    if (pty >= kb) {
         // L panel tile i = pt.y + 1 > kb
-        const int i0 = (pt.y + 1) * TB;
+        const int i0 = (pty + 1) * TB;
         gemm_accum<true, true>(acc, Lg + (size_t)i0 * Mp, Mp, Lg + (size_t)r0 * Mp, Mp, 0, r0, nullptr, sm);
         ACC_FOREACH(true, true, 0, 0, {
-            const double2 k = *reinterpret_cast<const double2*>(Lg + (size_t)(i0 + row) * Mp + r0 + col);
+            const double2 k = __ldcg(reinterpret_cast<const double2*>(Lg + (size_t)(i0 + row) * Mp + r0 + col));
             *reinterpret_cast<double2*>(tmp + row * TB + col) = make_double2(k.x - v0, k.y - v1);
         })
         __syncthreads();
@@ -593,7 +604,7 @@ k_chol_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, i
         })
     } else {
         // Linv row tile j = pt.y < kb
-        const int j0 = pt.y * TB;
+        const int j0 = pty * TB;
         gemm_accum<true, false>(acc, Lg + (size_t)r0 * Mp, Mp, Li + j0, Mp, j0, r0, nullptr, sm);
         ACC_FOREACH(true, false, 0, 0, { *reinterpret_cast<double2*>(tmp + row * TB + col) = make_double2(v0, v1); })
         __syncthreads();
@@ -606,6 +617,69 @@ k_chol_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, i
         ACC_FOREACH(true, false, 0, 0, {
             *reinterpret_cast<double2*>(Li + (size_t)(r0 + row) * Mp + j0 + col) = make_double2(-v0, -v1);
         })
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS)
+k_chol_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, int kb, GpParams prm,
+             double* __restrict__ ws, double* __restrict__ scratch) {
+    extern __shared__ __align__(16) unsigned char smem_panel[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_panel);
+    const int2 pt = ptiles[blockIdx.x];
+    const Region R = regs[pt.x];
+    panel_tile(R, prm.D, kb, pt.y, ws, scratch + (size_t)blockIdx.x * TB * TB, sm);
+}
+
+// The whole blocked sweep (all block steps, all regions of a group) as ONE persistent launch: CTAs
+// draw (region, step, tile) tasks from a list sorted by step through an atomic ticket and wait on
+// per-(region, step) completion counters, so every region advances at its own pace and no SM idles
+// between steps.  A task only ever waits for tasks with a smaller ticket, which are running or done,
+// hence no deadlock however few CTAs are resident.  Counters grow by nb per (region, step) and sweep
+// ("epoch"), so they are never reset.
+__global__ void __launch_bounds__(GEMM_THREADS)
+k_chol_sweep(const Region* __restrict__ regs, const int4* __restrict__ tasks, int n_tasks, int nbmax,
+             int* __restrict__ done, int* __restrict__ ticket, int epoch, GpParams prm, double* __restrict__ ws,
+             double* __restrict__ scratch, int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_sweep[];
+    __shared__ int s_task;
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_sweep);
+    double* tmp = scratch + (size_t)blockIdx.x * TB * TB;
+    const int tid = threadIdx.x;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_task = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int task = s_task;
+        if (task >= n_tasks) break;
+        const int4 t = tasks[task];
+        const Region R = regs[t.x];
+        const int kb = t.y;
+        int* cnt = done + (size_t)t.x * nbmax + kb;
+        if (tid == 0) {
+            const volatile int* flag = nullptr;
+            int need = 0;
+            if (t.z < 0) {
+                if (kb > 0) {
+                    flag = cnt - 1;                 // step kb-1 of this region complete in this sweep
+                    need = epoch * R.nb;
+                }
+            } else {
+                flag = cnt;                         // this step's diagonal tile done
+                need = (epoch - 1) * R.nb + 1;
+            }
+            if (flag) {
+                while (*flag < need) __nanosleep(40);
+                __threadfence();
+            }
+        }
+        __syncthreads();
+        if (t.z < 0)
+            diag_step(R, prm.D, kb, ws, status, smem_sweep);
+        else
+            panel_tile(R, prm.D, kb, t.z, ws, tmp, sm);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(cnt, 1);
     }
 }
 
@@ -911,9 +985,13 @@ size_t region_doubles(const Region& r, int D) {
     return (size_t)gapro_align_up((size_t)make_layout(r.Mp, r.Np, r.Wp, D).total, 32);
 }
 
-// bytes of tables + descriptors + panel scratch for a set of regions
+// bytes of tables + descriptors + sweep state + panel scratch for a set of regions
+constexpr int SWEEP_MAX_GRID = 320;
+constexpr int SWEEP_TICKETS = 4096;
+
 size_t aux_bytes(const std::vector<Region>& rs) {
     size_t full = 0, lower = 0, wide = 0, rows = 0, rowsp = 0, panel = 0;
+    int nbmax = 0;
     for (const Region& r : rs) {
         full += (size_t)r.nb * r.nb;
         lower += (size_t)r.nb * (r.nb + 1) / 2;
@@ -921,13 +999,18 @@ size_t aux_bytes(const std::vector<Region>& rs) {
         rows += r.nb;
         rowsp += r.Np / TB;
         panel += r.nb - 1;
+        nbmax = std::max(nbmax, r.nb);
     }
+    const size_t scratch_tiles = std::max(panel, std::min(full, (size_t)SWEEP_MAX_GRID));
     size_t b = 0;
     b += gapro_align_up(rs.size() * sizeof(Region), 256);
     b += gapro_align_up(full * 16, 256) + gapro_align_up(lower * 16, 256) + gapro_align_up(wide * 16, 256);
     b += gapro_align_up(rows * 8, 256) + gapro_align_up(rowsp * 8, 256) + gapro_align_up(panel * 8, 256);
-    b += gapro_align_up(panel * TB * TB * 8, 256);
-    return b + 256;
+    b += gapro_align_up(full * 16, 256);                                  // sweep task list
+    b += gapro_align_up(rs.size() * (size_t)nbmax * 4, 256);             // sweep completion counters
+    b += gapro_align_up((size_t)SWEEP_TICKETS * 4, 256);                  // sweep tickets
+    b += gapro_align_up(scratch_tiles * TB * TB * 8, 256);
+    return b + 256 + (size_t)4 * 12 * 256;   // + per-group table alignment slack (MAX_GROUPS side streams)
 }
 
 thread_local int64_t g_launches = 0;
@@ -937,6 +1020,10 @@ struct ChunkTables {
     int4 *full, *lower, *wide;
     int2 *rows, *rowsp, *panel;
     double* scratch;
+    int4* sweep_tasks;
+    int* sweep_done;
+    int* sweep_tickets;
+    int n_sweep, sweep_grid;
     int n_full, n_lower, n_wide, n_rows, n_rowsp;
     std::vector<int> cnt_gt;        // cnt_gt[kb] = #regions with nb > kb
     std::vector<int> panel_prefix;  // panel tiles of the first cnt_gt[kb] regions
@@ -1004,6 +1091,8 @@ struct Driver {
     int n_regs;
     ChunkTables tb;
     PredictOut po;
+    int epoch = 0;
+    bool use_sweep = true;
 
     GpParams params(int step, int predict) const {
         GpParams p;
@@ -1036,6 +1125,14 @@ struct Driver {
     }
 
     void cholesky(const GpParams& p) {
+        if (use_sweep && epoch + 1 < SWEEP_TICKETS) {
+            ++epoch;
+            k_chol_sweep<<<tb.sweep_grid, GEMM_THREADS, DIAG_SMEM, stream>>>(tb.regs, tb.sweep_tasks, tb.n_sweep, tb.nbmax,
+                                                                           tb.sweep_done, tb.sweep_tickets + epoch, epoch,
+                                                                           p, ws, tb.scratch, po.status);
+            ++g_launches;
+            return;
+        }
         for (int kb = 0; kb < tb.nbmax; ++kb) {
             const int live = tb.cnt_gt[kb];
             if (live <= 0) break;
@@ -1141,6 +1238,30 @@ int setup_chunk(std::vector<Region>& rs, char* aux, cudaStream_t stream, ChunkTa
     tb.rows = (int2*)put(rows.data(), rows.size() * 8);
     tb.rowsp = (int2*)put(rowsp.data(), rowsp.size() * 8);
     tb.panel = (int2*)put(panel.data(), panel.size() * 8);
+    // sweep tasks sorted by block step: all diagonal tiles of a step, then all its panel tiles
+    std::vector<int4> tasks;
+    tasks.reserve(full.size());
+    for (int kb = 0; kb < tb.nbmax; ++kb) {
+        const int live = tb.cnt_gt[kb];
+        for (int r = 0; r < live; ++r) tasks.push_back(make_int4(r, kb, -1, 0));
+        for (int r = 0; r < live; ++r)
+            for (int t = 0; t < rs[r].nb - 1; ++t) tasks.push_back(make_int4(r, kb, t, 0));
+    }
+    tb.sweep_tasks = (int4*)put(tasks.data(), tasks.size() * 16);
+    tb.n_sweep = (int)tasks.size();
+    tb.sweep_done = (int*)(aux + o);
+    {
+        const size_t bytes = gapro_align_up(rs.size() * (size_t)tb.nbmax * 4, 256);
+        cudaMemsetAsync(aux + o, 0, bytes, stream);
+        o += bytes;
+    }
+    tb.sweep_tickets = (int*)(aux + o);
+    {
+        const size_t bytes = gapro_align_up((size_t)SWEEP_TICKETS * 4, 256);
+        cudaMemsetAsync(aux + o, 0, bytes, stream);
+        o += bytes;
+    }
+    tb.sweep_grid = std::min(tb.n_sweep, SWEEP_MAX_GRID);
     tb.scratch = (double*)(aux + o);
     tb.n_full = (int)full.size();
     tb.n_lower = (int)lower.size();
@@ -1240,6 +1361,7 @@ static int set_kernel_attributes() {
     int rc = allow_smem(k_build, 3 * TB * 64 * 8);
     if (rc == GAPRO_OK) rc = allow_smem(k_chol_diag, DIAG_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_chol_panel, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_chol_sweep, DIAG_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_A>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_B>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GA>, GEMM_SMEM);
@@ -1260,7 +1382,6 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
     GAPRO_REQUIRE(D >= 1 && D <= 64, "gp: feature dimension %d not in [1, 64]", D);
     int rc = set_kernel_attributes();
     if (rc != GAPRO_OK) return rc;
-    const size_t group_slack = (size_t)MAX_GROUPS * 8 * 256;
     size_t pos = 0;
     while (pos < all.size()) {
         // greedy chunk: as many regions (already sorted by size) as fit in the workspace
@@ -1271,7 +1392,7 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             r.base = (long long)doubles;
             chunk.push_back(r);
             size_t nd = doubles + region_doubles(r, D);
-            if (nd * 8 + aux_bytes(chunk) + group_slack > ws_bytes) {
+            if (nd * 8 + aux_bytes(chunk) > ws_bytes) {
                 chunk.pop_back();
                 break;
             }
@@ -1301,6 +1422,7 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             d.ws = (double*)ws;
             d.n_regs = (int)groups[g].size();
             d.po = po;
+            if (const char* e = getenv("GAPRO_CHOL_SWEEP")) d.use_sweep = atoi(e) != 0;
             rc = setup_chunk(groups[g], aux, stream, d.tb);     // uploads on the caller's stream, then syncs
             if (rc != GAPRO_OK) return rc;
             aux += aux_bytes(groups[g]);

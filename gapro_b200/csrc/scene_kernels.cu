@@ -303,6 +303,20 @@ extern "C" int gapro_floor_boxes(const double* xyz, const int64_t* pt_off_dev, c
 // =============================================================================================
 // A + A' — containment + occupancy (gen_ps_utils.py:349-351, 359-363), one warp per superpoint
 // =============================================================================================
+// One warp per superpoint.  Pass 1 gathers the superpoint's points and reduces their extent; pass 2
+// lets lane b classify box 32w+b against that extent: "contains" (every point inside: count = size)
+// and "disjoint" (count = 0) are decided without touching the points again — exact, because the
+// containment test is a conjunction of per-axis interval tests — and only boxes that cut through the
+// superpoint are counted point by point with a warp ballot.
+__device__ __forceinline__ double warp_min(double v) {
+    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+
 template <int WORDS>
 __global__ void __launch_bounds__(256)
 k_occupancy(const double* __restrict__ xyz, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
@@ -317,48 +331,72 @@ k_occupancy(const double* __restrict__ xyz, const int32_t* __restrict__ perm, co
     const int b0 = box_off[sc];
     const int nb = box_off[sc + 1] - b0;
     const int start = seg_off[g], end = seg_off[g + 1];
-    int acc[WORDS];
-#pragma unroll
-    for (int w = 0; w < WORDS; ++w) acc[w] = 0;
+    const int cnt = end - start;
 
-    for (int base = start; base < end; base += 32) {
-        const int k = base + lane;
-        const bool valid = k < end;
-        double x = 0, y = 0, z = 0;
-        if (valid) {
-            const int64_t p = perm[k];
-            x = xyz[3 * p];
-            y = xyz[3 * p + 1];
-            z = xyz[3 * p + 2];
-        }
-#pragma unroll
-        for (int w = 0; w < WORDS; ++w) {
-            const int nbw = min(32, nb - 32 * w);
-            uint32_t mask = 0;
-            for (int bb = 0; bb < nbw; ++bb) {
-                const double* bx = boxes + 6 * (size_t)(b0 + 32 * w + bb);   // warp-uniform address: broadcast
-                // margins in float64 on the float64 boxes (gen_ps_utils.py:350)
-                bool in = valid && x >= __dsub_rn(bx[0], margin) && y >= __dsub_rn(bx[1], margin) &&
-                          z >= __dsub_rn(bx[2], margin) && x <= __dadd_rn(bx[3], margin) &&
-                          y <= __dadd_rn(bx[4], margin) && z <= __dadd_rn(bx[5], margin);
-                mask |= (uint32_t)in << bb;
-            }
-            // ballot-transpose: lane bb accumulates the count of box 32w+bb
-            for (int bb = 0; bb < nbw; ++bb) {
-                int c = __popc(__ballot_sync(FULL_MASK, (mask >> bb) & 1u));
-                if (lane == bb) acc[w] += c;
-            }
-        }
+    // pass 1: extent of the superpoint; the first 32 points stay in registers
+    double px = 0, py = 0, pz = 0;
+    const bool pvalid = start + lane < end;
+    if (pvalid) {
+        const int64_t p = perm[start + lane];
+        px = xyz[3 * p];
+        py = xyz[3 * p + 1];
+        pz = xyz[3 * p + 2];
     }
-    const float fcnt = (float)(end - start);
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double lx = pvalid ? px : INF, ly = pvalid ? py : INF, lz = pvalid ? pz : INF;
+    double hx = pvalid ? px : -INF, hy = pvalid ? py : -INF, hz = pvalid ? pz : -INF;
+    for (int k = start + 32 + lane; k < end; k += 32) {
+        const int64_t p = perm[k];
+        const double x = xyz[3 * p], y = xyz[3 * p + 1], z = xyz[3 * p + 2];
+        lx = fmin(lx, x); ly = fmin(ly, y); lz = fmin(lz, z);
+        hx = fmax(hx, x); hy = fmax(hy, y); hz = fmax(hz, z);
+    }
+    lx = warp_min(lx); ly = warp_min(ly); lz = warp_min(lz);
+    hx = warp_max(hx); hy = warp_max(hy); hz = warp_max(hz);
+
+    const float fcnt = (float)cnt;
     uint32_t bits[WORDS];
     int total = 0;
 #pragma unroll
     for (int w = 0; w < WORDS; ++w) {
-        bool occ = (32 * w + lane < nb) && (__fdiv_rn((float)acc[w], fcnt) >= thresh);
+        const int b = 32 * w + lane;
+        int count = 0;
+        bool partial = false;
+        if (b < nb) {
+            const double* bx = boxes + 6 * (size_t)(b0 + b);
+            // margins in float64 on the float64 boxes (gen_ps_utils.py:350)
+            const double l0 = __dsub_rn(bx[0], margin), l1 = __dsub_rn(bx[1], margin), l2 = __dsub_rn(bx[2], margin);
+            const double h0 = __dadd_rn(bx[3], margin), h1 = __dadd_rn(bx[4], margin), h2 = __dadd_rn(bx[5], margin);
+            const bool contains = lx >= l0 && ly >= l1 && lz >= l2 && hx <= h0 && hy <= h1 && hz <= h2;
+            const bool disjoint = hx < l0 || hy < l1 || hz < l2 || lx > h0 || ly > h1 || lz > h2;
+            count = contains ? cnt : 0;
+            partial = !contains && !disjoint;
+        }
+        uint32_t pmask = __ballot_sync(FULL_MASK, partial);
+        while (pmask) {
+            const int bb = __ffs(pmask) - 1;
+            pmask &= pmask - 1;
+            const double* bx = boxes + 6 * (size_t)(b0 + 32 * w + bb);      // warp-uniform address
+            const double l0 = __dsub_rn(bx[0], margin), l1 = __dsub_rn(bx[1], margin), l2 = __dsub_rn(bx[2], margin);
+            const double h0 = __dadd_rn(bx[3], margin), h1 = __dadd_rn(bx[4], margin), h2 = __dadd_rn(bx[5], margin);
+            bool in = pvalid && px >= l0 && py >= l1 && pz >= l2 && px <= h0 && py <= h1 && pz <= h2;
+            int c = __popc(__ballot_sync(FULL_MASK, in));
+            for (int base = start + 32; base < end; base += 32) {
+                const int k = base + lane;
+                in = false;
+                if (k < end) {
+                    const int64_t p = perm[k];
+                    const double x = xyz[3 * p], y = xyz[3 * p + 1], z = xyz[3 * p + 2];
+                    in = x >= l0 && y >= l1 && z >= l2 && x <= h0 && y <= h1 && z <= h2;
+                }
+                c += __popc(__ballot_sync(FULL_MASK, in));
+            }
+            if (lane == bb) count = c;
+        }
+        const bool occ = (b < nb) && (__fdiv_rn((float)count, fcnt) >= thresh);
         bits[w] = __ballot_sync(FULL_MASK, occ);
         total += __popc(bits[w]);
-        if (cnt_in) cnt_in[((size_t)g * WORDS + w) * 32 + lane] = acc[w];
+        if (cnt_in) cnt_in[((size_t)g * WORDS + w) * 32 + lane] = count;
         if (lane == 0) occ_bits[(size_t)g * WORDS + w] = bits[w];
     }
     if (lane == 0) {
@@ -425,27 +463,52 @@ extern "C" int gapro_occupancy(const double* xyz, const int32_t* perm, const int
 // =============================================================================================
 // B — feature pooling (gen_ps_utils.py:357): float32 sum in point-index order, / float32 count
 // =============================================================================================
+// One warp per superpoint.  Lane (p, d) gathers feature d of point p of the current group of
+// P = 32 / D points (several independent gathers in flight per superpoint); the float32 adds are
+// then replayed strictly in point order through warp shuffles, so the sum is the index-ordered
+// float32 sum of torch_scatter's CPU kernel, bit for bit.
 __global__ void __launch_bounds__(256)
 k_pool_feats(const float* __restrict__ feats, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
              int s_total, int D, float* __restrict__ out) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)s_total * D) return;
-    const int g = (int)(t / D), d = (int)(t % D);
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= s_total) return;
     const int start = seg_off[g], end = seg_off[g + 1];
-    float acc = 0.0f;
-    int k = start;
-    for (; k + 4 <= end; k += 4) {     // four independent gathers in flight, adds strictly in order
-        float v0 = feats[(int64_t)perm[k] * D + d];
-        float v1 = feats[(int64_t)perm[k + 1] * D + d];
-        float v2 = feats[(int64_t)perm[k + 2] * D + d];
-        float v3 = feats[(int64_t)perm[k + 3] * D + d];
-        acc = __fadd_rn(acc, v0);
-        acc = __fadd_rn(acc, v1);
-        acc = __fadd_rn(acc, v2);
-        acc = __fadd_rn(acc, v3);
+    const float fcnt = (float)(end - start);
+    if (D <= 16) {
+        const int P = 32 / D;
+        const int p = lane / D, d = lane - p * D;
+        const bool worker = p < P;
+        float acc = 0.0f;
+        for (int base = start; base < end; base += 2 * P) {
+            // two groups of P points in flight
+            const int k0 = base + p, k1 = base + P + p;
+            float v0 = 0.0f, v1 = 0.0f;
+            if (worker && k0 < end) v0 = feats[(int64_t)perm[k0] * D + d];
+            if (worker && k1 < end) v1 = feats[(int64_t)perm[k1] * D + d];
+            const int n0 = min(P, end - base), n1 = min(P, max(end - base - P, 0));
+            for (int q = 0; q < n0; ++q) acc = __fadd_rn(acc, __shfl_sync(FULL_MASK, v0, q * D + d));
+            for (int q = 0; q < n1; ++q) acc = __fadd_rn(acc, __shfl_sync(FULL_MASK, v1, q * D + d));
+        }
+        if (lane < D) out[(int64_t)g * D + d] = __fdiv_rn(acc, fcnt);
+    } else {
+        for (int d = lane; d < D; d += 32) {
+            float acc = 0.0f;
+            int k = start;
+            for (; k + 4 <= end; k += 4) {     // four independent gathers in flight, adds strictly in order
+                const float v0 = feats[(int64_t)perm[k] * D + d];
+                const float v1 = feats[(int64_t)perm[k + 1] * D + d];
+                const float v2 = feats[(int64_t)perm[k + 2] * D + d];
+                const float v3 = feats[(int64_t)perm[k + 3] * D + d];
+                acc = __fadd_rn(acc, v0);
+                acc = __fadd_rn(acc, v1);
+                acc = __fadd_rn(acc, v2);
+                acc = __fadd_rn(acc, v3);
+            }
+            for (; k < end; ++k) acc = __fadd_rn(acc, feats[(int64_t)perm[k] * D + d]);
+            out[(int64_t)g * D + d] = __fdiv_rn(acc, fcnt);
+        }
     }
-    for (; k < end; ++k) acc = __fadd_rn(acc, feats[(int64_t)perm[k] * D + d]);
-    out[t] = __fdiv_rn(acc, (float)(end - start));
 }
 
 extern "C" int gapro_pool_feats(const float* feats, const int32_t* perm, const int32_t* seg_off, int32_t s_total,
@@ -453,8 +516,7 @@ extern "C" int gapro_pool_feats(const float* feats, const int32_t* perm, const i
     cudaStream_t stream = (cudaStream_t)stream_;
     GAPRO_REQUIRE(feats && perm && seg_off && out, "gapro_pool_feats: null pointer");
     GAPRO_REQUIRE(s_total > 0 && D > 0, "gapro_pool_feats: empty input");
-    int64_t total = (int64_t)s_total * D;
-    k_pool_feats<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(feats, perm, seg_off, s_total, D, out);
+    k_pool_feats<<<(unsigned)((s_total + 7) / 8), 256, 0, stream>>>(feats, perm, seg_off, s_total, D, out);
     GAPRO_KERNEL_CHECK();
     return GAPRO_OK;
 }
@@ -528,7 +590,8 @@ k_resolve_spp(const uint32_t* __restrict__ occ_bits, const int32_t* __restrict__
               const int32_t* __restrict__ ev_gp_off, const int32_t* __restrict__ lists_idx,
               const float* __restrict__ gp_conf, const uint8_t* __restrict__ gp_label, const float* __restrict__ gp_mu,
               const float* __restrict__ gp_var, int32_t* __restrict__ sem_spp, int32_t* __restrict__ inst_spp,
-              float* __restrict__ prob_spp, float* __restrict__ mu_spp, float* __restrict__ var_spp) {
+              float* __restrict__ prob_spp, float* __restrict__ mu_spp, float* __restrict__ var_spp,
+              int4* __restrict__ packed_spp) {
     const int sc = blockIdx.x;
     const int g0 = spp_off[sc], g1 = spp_off[sc + 1];
     const int b0 = box_off[sc];
@@ -608,6 +671,7 @@ k_resolve_spp(const uint32_t* __restrict__ occ_bits, const int32_t* __restrict__
         if (inst_out >= nfg) inst_out = -100;
         sem_spp[g] = sem;
         inst_spp[g] = inst_out;
+        if (packed_spp) packed_spp[g] = make_int4(sem, inst_out, __float_as_int(prob_spp[g]), 0);
     }
 }
 
@@ -618,7 +682,8 @@ extern "C" int gapro_resolve_spp(const uint32_t* occ_bits, const int32_t* n_bbs,
                                  const int32_t* ev_b2, const int32_t* ev_list_off, const int32_t* ev_list_len,
                                  const int32_t* ev_gp_off, const int32_t* lists_idx, const float* gp_conf,
                                  const uint8_t* gp_label, const float* gp_mu, const float* gp_var, int32_t* sem_spp,
-                                 int32_t* inst_spp, float* prob_spp, float* mu_spp, float* var_spp, void* stream_) {
+                                 int32_t* inst_spp, float* prob_spp, float* mu_spp, float* var_spp, void* packed_spp,
+                                 void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GAPRO_REQUIRE(occ_bits && n_bbs && spp_off_dev && box_off_dev && boxes_vol && boxes_cls && n_fg && ev_off &&
                       sem_spp && inst_spp && prob_spp && mu_spp && var_spp,
@@ -627,7 +692,7 @@ extern "C" int gapro_resolve_spp(const uint32_t* occ_bits, const int32_t* n_bbs,
     k_resolve_spp<<<n_scenes, 512, 0, stream>>>(occ_bits, n_bbs, words, spp_off_dev, box_off_dev, boxes_vol, boxes_cls,
                                                 n_fg, instance_classes, ev_off, ev_kind, ev_b1, ev_b2, ev_list_off,
                                                 ev_list_len, ev_gp_off, lists_idx, gp_conf, gp_label, gp_mu, gp_var,
-                                                sem_spp, inst_spp, prob_spp, mu_spp, var_spp);
+                                                sem_spp, inst_spp, prob_spp, mu_spp, var_spp, (int4*)packed_spp);
     GAPRO_KERNEL_CHECK();
     return GAPRO_OK;
 }
@@ -636,42 +701,40 @@ extern "C" int gapro_resolve_spp(const uint32_t* occ_bits, const int32_t* n_bbs,
 // E — broadcast to points (gen_ps_utils.py:478-480)
 // =============================================================================================
 __global__ void __launch_bounds__(256)
-k_broadcast(const int32_t* __restrict__ spp_gid, int64_t n, const int32_t* __restrict__ sem_spp,
-            const int32_t* __restrict__ inst_spp, const float* __restrict__ prob_spp, int32_t* __restrict__ sem,
-            int32_t* __restrict__ inst, float* __restrict__ prob) {
-    // 4 points per thread, 128-bit loads/stores (n4 quads) + scalar tail
+k_broadcast(const int32_t* __restrict__ spp_gid, int64_t n, const int4* __restrict__ packed_spp,
+            int32_t* __restrict__ sem, int32_t* __restrict__ inst, float* __restrict__ prob) {
+    // 4 points per thread: one 128-bit load of ids, four 128-bit gathers of (sem, inst, prob) records
+    // from the L2-resident per-superpoint table, three 128-bit stores; scalar tail
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t n4 = n >> 2;
     if (q < n4) {
-        int4 g = reinterpret_cast<const int4*>(spp_gid)[q];
-        int4 s = make_int4(sem_spp[g.x], sem_spp[g.y], sem_spp[g.z], sem_spp[g.w]);
-        int4 i = make_int4(inst_spp[g.x], inst_spp[g.y], inst_spp[g.z], inst_spp[g.w]);
-        float4 p = make_float4(prob_spp[g.x], prob_spp[g.y], prob_spp[g.z], prob_spp[g.w]);
-        reinterpret_cast<int4*>(sem)[q] = s;
-        reinterpret_cast<int4*>(inst)[q] = i;
-        reinterpret_cast<float4*>(prob)[q] = p;
+        const int4 g = __ldcs(reinterpret_cast<const int4*>(spp_gid) + q);
+        const int4 a = __ldg(packed_spp + g.x), b = __ldg(packed_spp + g.y), c = __ldg(packed_spp + g.z),
+                   d = __ldg(packed_spp + g.w);
+        __stcs(reinterpret_cast<int4*>(sem) + q, make_int4(a.x, b.x, c.x, d.x));
+        __stcs(reinterpret_cast<int4*>(inst) + q, make_int4(a.y, b.y, c.y, d.y));
+        __stcs(reinterpret_cast<int4*>(prob) + q, make_int4(a.z, b.z, c.z, d.z));
     } else if (q == n4) {
         for (int64_t k = n4 << 2; k < n; ++k) {
-            int g = spp_gid[k];
-            sem[k] = sem_spp[g];
-            inst[k] = inst_spp[g];
-            prob[k] = prob_spp[g];
+            const int4 a = packed_spp[spp_gid[k]];
+            sem[k] = a.x;
+            inst[k] = a.y;
+            prob[k] = __int_as_float(a.z);
         }
     }
 }
 
-extern "C" int gapro_broadcast_labels(const int32_t* spp_gid, int64_t n_points, const int32_t* sem_spp,
-                                      const int32_t* inst_spp, const float* prob_spp, int32_t* sem, int32_t* inst,
-                                      float* prob, void* stream_) {
+extern "C" int gapro_broadcast_labels(const int32_t* spp_gid, int64_t n_points, const void* packed_spp, int32_t* sem,
+                                      int32_t* inst, float* prob, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    GAPRO_REQUIRE(spp_gid && sem_spp && inst_spp && prob_spp && sem && inst && prob, "gapro_broadcast_labels: null pointer");
+    GAPRO_REQUIRE(spp_gid && packed_spp && sem && inst && prob, "gapro_broadcast_labels: null pointer");
     GAPRO_REQUIRE(n_points > 0, "gapro_broadcast_labels: empty input");
     GAPRO_REQUIRE(((uintptr_t)spp_gid % 16 == 0) && ((uintptr_t)sem % 16 == 0) && ((uintptr_t)inst % 16 == 0) &&
-                      ((uintptr_t)prob % 16 == 0),
-                  "gapro_broadcast_labels: point arrays must be 16-byte aligned");
+                      ((uintptr_t)prob % 16 == 0) && ((uintptr_t)packed_spp % 16 == 0),
+                  "gapro_broadcast_labels: arrays must be 16-byte aligned");
     int64_t threads = (n_points >> 2) + 1;
-    k_broadcast<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(spp_gid, n_points, sem_spp, inst_spp, prob_spp,
-                                                                       sem, inst, prob);
+    k_broadcast<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(spp_gid, n_points, (const int4*)packed_spp, sem,
+                                                                       inst, (float*)prob);
     GAPRO_KERNEL_CHECK();
     return GAPRO_OK;
 }

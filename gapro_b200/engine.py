@@ -249,6 +249,7 @@ class GaproEngine:
         prob_spp = torch.empty(St, dtype=torch.float32, device=dev)
         mu_spp = torch.empty(St, dtype=torch.float32, device=dev)
         var_spp = torch.empty(St, dtype=torch.float32, device=dev)
+        packed_spp = torch.empty((St, 4), dtype=torch.int32, device=dev)
         d_ev = [self._dev(a) for a in (ev_off, ev_kind.astype(np.int32), ev_b1.astype(np.int32),
                                        ev_b2.astype(np.int32), ev_list_off.astype(np.int32),
                                        inter_len.astype(np.int32), ev_gp_off)]
@@ -259,21 +260,19 @@ class GaproEngine:
                                          n_fg_dev.data_ptr(), int(instance_classes), ns, *[t.data_ptr() for t in d_ev],
                                          lists_idx.data_ptr(), gp_conf.data_ptr(), gp_label.data_ptr(),
                                          gp_mu.data_ptr(), gp_var.data_ptr(), sem_spp.data_ptr(), inst_spp.data_ptr(),
-                                         prob_spp.data_ptr(), mu_spp.data_ptr(), var_spp.data_ptr(), stream),
-                   "gapro_resolve_spp")
+                                         prob_spp.data_ptr(), mu_spp.data_ptr(), var_spp.data_ptr(),
+                                         packed_spp.data_ptr(), stream), "gapro_resolve_spp")
         sem = torch.empty(N, dtype=torch.int32, device=dev)
         inst = torch.empty(N, dtype=torch.int32, device=dev)
         prob = torch.empty(N, dtype=torch.float32, device=dev)
-        _lib.check(lib.gapro_broadcast_labels(spp_gid.data_ptr(), N, sem_spp.data_ptr(), inst_spp.data_ptr(),
-                                              prob_spp.data_ptr(), sem.data_ptr(), inst.data_ptr(), prob.data_ptr(),
-                                              stream), "gapro_broadcast_labels")
+        _lib.check(lib.gapro_broadcast_labels(spp_gid.data_ptr(), N, packed_spp.data_ptr(), sem.data_ptr(),
+                                              inst.data_ptr(), prob.data_ptr(), stream), "gapro_broadcast_labels")
         n_launch += 2
 
         if keep:
             self.last = dict(xyz=xyz, feats=feats, perm=perm, seg_off=seg_off, spp_gid=spp_gid, spp_off_dev=spp_off_dev,
                              box_off_dev=box_off_dev, boxes=boxes, occ_bits=occ_bits, n_bbs=n_bbs, excl_cnt=excl_cnt,
-                             inter_cnt=inter_cnt, feats_spp=feats_spp, sem_spp=sem_spp, inst_spp=inst_spp,
-                             prob_spp=prob_spp, sem=sem, inst=inst, prob=prob, ns=ns, St=St, Bt=Bt, N=N, D=D,
+                             inter_cnt=inter_cnt, feats_spp=feats_spp, packed_spp=packed_spp, sem=sem, inst=inst, prob=prob, ns=ns, St=St, Bt=Bt, N=N, D=D,
                              words=words, thresh=float(np.float32(thresh_spp_occu)))
         out = []
         for i in range(ns):

@@ -227,7 +227,9 @@ const char* gapro_gp_debug_layout_names(void);
  *   ev_list_off/ev_list_len dev int32[n_events]: the event's intersection list in lists_idx
  *   ev_gp_off   dev int32[n_events]: offset of the event's rows in the GP outputs (-1 for nest)
  *   boxes_cls dev int64[n_boxes]; n_fg dev int32[n_scenes] (#instance boxes per scene)
- *   out per superpoint: sem_spp/inst_spp int32, prob/mu/var float
+ *   out per superpoint: sem_spp/inst_spp int32, prob/mu/var float; packed_spp (optional, dev
+ *   int32[S_total,4], 16-byte aligned) receives the records (sem, inst, prob bits, 0) that
+ *   gapro_broadcast_labels gathers with one 128-bit load per point
  */
 int gapro_resolve_spp(const uint32_t* occ_bits, const int32_t* n_bbs, int32_t words, const int32_t* spp_off_dev,
                       const int32_t* box_off_dev, const double* boxes_vol, const int64_t* boxes_cls,
@@ -236,16 +238,16 @@ int gapro_resolve_spp(const uint32_t* occ_bits, const int32_t* n_bbs, int32_t wo
                       const int32_t* ev_list_off, const int32_t* ev_list_len, const int32_t* ev_gp_off,
                       const int32_t* lists_idx, const float* gp_conf, const uint8_t* gp_label, const float* gp_mu,
                       const float* gp_var, int32_t* sem_spp, int32_t* inst_spp, float* prob_spp, float* mu_spp,
-                      float* var_spp, void* stream);
+                      float* var_spp, void* packed_spp, void* stream);
 
 /* ---------------------------------------------------------------------------
  * E — broadcast to points.  Replaces gen_ps_utils.py:478-480
  * (sem[spp], inst[spp], prob[spp]; mu/var stay per superpoint, :482).
- *   sem/inst dev int32[n], prob dev float[n]
+ *   packed_spp: the per-superpoint records written by gapro_resolve_spp; sem/inst dev int32[n],
+ *   prob dev float[n]; all point arrays 16-byte aligned
  */
-int gapro_broadcast_labels(const int32_t* spp_gid, int64_t n_points, const int32_t* sem_spp,
-                           const int32_t* inst_spp, const float* prob_spp, int32_t* sem, int32_t* inst,
-                           float* prob, void* stream);
+int gapro_broadcast_labels(const int32_t* spp_gid, int64_t n_points, const void* packed_spp, int32_t* sem,
+                           int32_t* inst, float* prob, void* stream);
 
 #ifdef __cplusplus
 }
