@@ -466,114 +466,119 @@ k_build(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParam
 }
 
 // ---------------------------------------------------------------------------------------------
-// blocked left-looking Cholesky with the inverse factor, block step kb
-//   diag : C = K[kb,kb] - sum_{j<kb} L[kb,j] L[kb,j]^T ; L_kk = chol(C) ; Linv_kk = L_kk^-1
-//   panel: L[i,kb] = (K[i,kb] - sum_{j<kb} L[i,j] L[kb,j]^T) Linv_kk^T          (i > kb)
-//          Linv[kb,j] = -Linv_kk sum_{k=j..kb-1} L[kb,k] Linv[k,j]              (j < kb)
+// Blocked RIGHT-looking Cholesky with the inverse factor built alongside.  Block step kb is three
+// short launches whose tiles all contract over a single 64-wide block, so the critical path of a
+// region with nb blocks is nb * (diag + panel + update) instead of growing with nb^2:
+//   diag  : L_kk = chol(K[kb,kb]) ; Linv_kk = L_kk^-1                      (tile already updated)
+//   panel : L[i,kb]    = K[i,kb] Linv_kk^T                                 (i > kb)
+//           Linv[kb,j] = -Linv_kk S[kb,j]                                  (j < kb)
+//   update: K[i,j] -= L[i,kb] L[j,kb]^T                                    (i >= j > kb)
+//           S[i,j] (+)= L[i,kb] Linv[kb,j]                                 (i > kb >= j; '=' when j == kb)
+// S[i,j] = sum_{k=j..kb} L[i,k] Linv[k,j] accumulates in place in the strictly-lower tiles of the
+// Linv buffer until step i turns it into Linv[i,j].
 // ---------------------------------------------------------------------------------------------
 constexpr int LDS_ = TB + 1;
-constexpr int DIAG_SMEM = GEMM_SMEM + TB * LDS_ * (int)sizeof(double);
-static_assert((TB * LDS_ + 3 * TB) * sizeof(double) <= sizeof(GemmSmem), "inverse tile + scratch must fit in the stages");
+constexpr int DIAG_SMEM = (2 * TB * LDS_ + 2 * TB) * (int)sizeof(double);
 
-__device__ __forceinline__ void bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
-
-// Diagonal step.  The 64x64 factorisation and the triangular inverse are register-resident and
-// fully unrolled: thread r of warps 0-1 owns row r (then column r of the inverse); one named
-// barrier per column, pivots through rsqrt instead of sqrt + divide.
-__device__ __forceinline__ void diag_step(const Region& R, int D, int kb, double* __restrict__ ws,
-                                          int32_t* __restrict__ status, unsigned char* smem_diag) {
-    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_diag);
-    double* sL = reinterpret_cast<double*>(smem_diag + sizeof(GemmSmem));
-    double* sX = reinterpret_cast<double*>(smem_diag);   // aliases the GEMM stages (dead after the product)
-    double* colbuf = sX + TB * LDS_;                     // [2][64]
-    double* dinv = colbuf + 2 * TB;                      // [64]
-    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
+// 64x64 factorisation + triangular inverse in shared memory.  Small loop bodies (no instruction
+// cache pressure), explicit 4-way batching so the shared-memory latency overlaps.
+__global__ void __launch_bounds__(GEMM_THREADS)
+k_rl_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __restrict__ ws, int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_diag[];
+    double* sL = reinterpret_cast<double*>(smem_diag);   // [64][65] tile, then L
+    double* sX = sL + TB * LDS_;                         // [64][65] right-hand sides, then L^-1
+    double* lc = sX + TB * LDS_;                         // [64] current column of L
+    double* dinv = lc + TB;                              // [64] 1 / L[k][k]
+    const Region R = regs[blockIdx.x];
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
     double* base = ws + R.base;
     const int Mp = R.Mp;
     double* Lg = base + lay.L;
+    double* Li = base + lay.Linv;
     const int r0 = kb * TB;
     const int tid = threadIdx.x;
-    {
-        double acc[4][4][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        gemm_accum<true, true>(acc, Lg + (size_t)r0 * Mp, Mp, Lg + (size_t)r0 * Mp, Mp, 0, r0, nullptr, sm);
-        ACC_FOREACH(true, true, 0, 0, {
-            const double2 k = __ldcg(reinterpret_cast<const double2*>(Lg + (size_t)(r0 + row) * Mp + r0 + col));
-            sL[row * LDS_ + col] = k.x - v0;
-            sL[row * LDS_ + col + 1] = k.y - v1;
-        })
-    }
-    __syncthreads();
-    if (tid < TB) {
-        const int r = tid;
-        double a[TB];
-#pragma unroll
-        for (int k = 0; k < TB; ++k) a[k] = sL[r * LDS_ + k];
-        bool bad = false;
-#pragma unroll
-        for (int c = 0; c < TB; ++c) {
-            double* col = colbuf + (c & 1) * TB;
-            col[r] = a[c];
-            bar64();
-            double piv = col[c];
-            if (!(piv > 0.0)) {
-                bad = true;
-                piv = 1.0;
-            }
-            const double rs = rsqrt(piv);
-            const double f = a[c] * (rs * rs);
-#pragma unroll
-            for (int cc = c + 1; cc < TB; ++cc) {
-                const double t = fma(-f, col[cc], a[cc]);
-                a[cc] = (cc <= r) ? t : a[cc];
-            }
-            a[c] = (r >= c) ? a[c] * rs : 0.0;
-            if (r == c) dinv[c] = rs;
-        }
-        if (bad && r == 0) atomicOr(status + R.orig, GAPRO_GP_NOT_PSD);
-#pragma unroll
-        for (int k = 0; k < TB; ++k) sL[r * LDS_ + k] = a[k];
-        bar64();
-        // column r of X = L^-1 by forward substitution; entries above the diagonal come out as 0
-        double x[TB];
-#pragma unroll
-        for (int q = 0; q < TB; ++q) {
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int k = 0; k < q; ++k) {
-                if (k & 1)
-                    s1 = fma(sL[q * LDS_ + k], x[k], s1);
-                else
-                    s0 = fma(sL[q * LDS_ + k], x[k], s0);
-            }
-            x[q] = (q == r) ? dinv[q] : -(s0 + s1) * dinv[q];
-        }
-#pragma unroll
-        for (int q = 0; q < TB; ++q) sX[q * LDS_ + r] = x[q];
-    }
-    __syncthreads();
-    double* Li = base + lay.Linv;
     for (int e = tid; e < TB * TB; e += GEMM_THREADS) {
         const int r = e >> 6, c = e & 63;
-        const bool low = c <= r;
-        Lg[(size_t)(r0 + r) * Mp + r0 + c] = low ? sL[r * LDS_ + c] : 0.0;
-        Li[(size_t)(r0 + r) * Mp + r0 + c] = low ? sX[r * LDS_ + c] : 0.0;
+        sL[r * LDS_ + c] = __ldcg(Lg + (size_t)(r0 + r) * Mp + r0 + c);
+        sX[r * LDS_ + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int r = tid & 63, half = tid >> 6;
+    bool bad = false;
+    for (int c = 0; c < TB; ++c) {
+        double piv = sL[c * LDS_ + c];
+        if (!(piv > 0.0)) {
+            bad = true;
+            piv = 1.0;
+        }
+        const double rs = rsqrt(piv);
+        double l = 0.0;
+        if (half == 0 && r >= c) l = sL[r * LDS_ + c] * rs;      // r == c: piv * rsqrt(piv) = sqrt(piv)
+        __syncthreads();                                         // everyone has read the pivot
+        if (half == 0 && r >= c) {
+            sL[r * LDS_ + c] = l;
+            lc[r] = l;
+            if (r == c) dinv[c] = rs;
+        }
+        __syncthreads();
+        if (r > c) {
+            const double lr = lc[r];
+            double* row = sL + r * LDS_;
+            int cc = c + 1 + half;
+            for (; cc + 6 <= r; cc += 8) {
+                const double v0 = row[cc], v1 = row[cc + 2], v2 = row[cc + 4], v3 = row[cc + 6];
+                const double w0 = lc[cc], w1 = lc[cc + 2], w2 = lc[cc + 4], w3 = lc[cc + 6];
+                row[cc] = fma(-lr, w0, v0);
+                row[cc + 2] = fma(-lr, w1, v1);
+                row[cc + 4] = fma(-lr, w2, v2);
+                row[cc + 6] = fma(-lr, w3, v3);
+            }
+            for (; cc <= r; cc += 2) row[cc] = fma(-lr, lc[cc], row[cc]);
+        }
+        __syncthreads();
+    }
+    if (bad && tid == 0) atomicOr(status + R.orig, GAPRO_GP_NOT_PSD);
+    // inverse by column-oriented forward substitution: thread (c, half) owns the rows of column c with
+    // parity `half`; b lives in sX[:, c]
+    {
+        const int c = r;
+        for (int k = 0; k < TB; ++k) {
+            const double xk = sX[k * LDS_ + c] * dinv[k];
+            __syncthreads();                     // both owners have read b[k]
+            if (half == 0) sX[k * LDS_ + c] = xk;
+            if (k >= c) {
+                int q = k + 1 + ((k + 1 + half) & 1);        // first row > k with parity `half`
+                for (; q + 6 < TB; q += 8) {
+                    const double b0 = sX[q * LDS_ + c], b1 = sX[(q + 2) * LDS_ + c], b2 = sX[(q + 4) * LDS_ + c],
+                                 b3 = sX[(q + 6) * LDS_ + c];
+                    const double l0 = sL[q * LDS_ + k], l1 = sL[(q + 2) * LDS_ + k], l2 = sL[(q + 4) * LDS_ + k],
+                                 l3 = sL[(q + 6) * LDS_ + k];
+                    sX[q * LDS_ + c] = fma(-l0, xk, b0);
+                    sX[(q + 2) * LDS_ + c] = fma(-l1, xk, b1);
+                    sX[(q + 4) * LDS_ + c] = fma(-l2, xk, b2);
+                    sX[(q + 6) * LDS_ + c] = fma(-l3, xk, b3);
+                }
+                for (; q < TB; q += 2) sX[q * LDS_ + c] = fma(-sL[q * LDS_ + k], xk, sX[q * LDS_ + c]);
+            }
+            __syncthreads();
+        }
+    }
+    for (int e = tid; e < TB * TB; e += GEMM_THREADS) {
+        const int rr = e >> 6, c = e & 63;
+        const bool low = c <= rr;
+        Lg[(size_t)(r0 + rr) * Mp + r0 + c] = low ? sL[rr * LDS_ + c] : 0.0;
+        Li[(size_t)(r0 + rr) * Mp + r0 + c] = low ? sX[rr * LDS_ + c] : 0.0;
     }
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS)
-k_chol_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __restrict__ ws, int32_t* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem_diag[];
-    const Region R = regs[blockIdx.x];
-    diag_step(R, prm.D, kb, ws, status, smem_diag);
-}
-
-__device__ __forceinline__ void panel_tile(const Region& R, int D, int kb, int pty, double* __restrict__ ws,
-                                           double* __restrict__ tmp, GemmSmem& sm) {
-    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
+k_rl_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, int kb, GpParams prm,
+           double* __restrict__ ws) {
+    extern __shared__ __align__(16) unsigned char smem_panel[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_panel);
+    const int2 pt = ptiles[blockIdx.x];
+    const Region R = regs[pt.x];
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
     double* base = ws + R.base;
     const int Mp = R.Mp;
     double* Lg = base + lay.L;
@@ -584,102 +589,64 @@ __device__ __forceinline__ void panel_tile(const Region& R, int D, int kb, int p
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    if (pty >= kb) {
-        // L panel tile i = pt.y + 1 > kb
-        const int i0 = (pty + 1) * TB;
-        gemm_accum<true, true>(acc, Lg + (size_t)i0 * Mp, Mp, Lg + (size_t)r0 * Mp, Mp, 0, r0, nullptr, sm);
-        ACC_FOREACH(true, true, 0, 0, {
-            const double2 k = __ldcg(reinterpret_cast<const double2*>(Lg + (size_t)(i0 + row) * Mp + r0 + col));
-            *reinterpret_cast<double2*>(tmp + row * TB + col) = make_double2(k.x - v0, k.y - v1);
-        })
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        // out[r,c] = sum_k tmp[r,k] Linv_kk[c,k]
-        gemm_accum<true, true>(acc, tmp, TB, Li + (size_t)r0 * Mp + r0, Mp, 0, TB, nullptr, sm);
+    if (pt.y >= kb) {
+        // L[i,kb] = K[i,kb] Linv_kk^T, in place: out[r,c] = sum_k K[i0+r][r0+k] Linv_kk[c][k]
+        const int i0 = (pt.y + 1) * TB;
+        gemm_accum<true, true>(acc, Lg + (size_t)i0 * Mp + r0, Mp, Li + (size_t)r0 * Mp + r0, Mp, 0, TB, nullptr, sm);
         ACC_FOREACH(true, true, 0, 0, {
             *reinterpret_cast<double2*>(Lg + (size_t)(i0 + row) * Mp + r0 + col) = make_double2(v0, v1);
         })
     } else {
-        // Linv row tile j = pt.y < kb
-        const int j0 = pty * TB;
-        gemm_accum<true, false>(acc, Lg + (size_t)r0 * Mp, Mp, Li + j0, Mp, j0, r0, nullptr, sm);
-        ACC_FOREACH(true, false, 0, 0, { *reinterpret_cast<double2*>(tmp + row * TB + col) = make_double2(v0, v1); })
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        // out[r,c] = -sum_k Linv_kk[r,k] tmp[k,c]
-        gemm_accum<true, false>(acc, Li + (size_t)r0 * Mp + r0, Mp, tmp, TB, 0, TB, nullptr, sm);
+        // Linv[kb,j] = -Linv_kk S[kb,j], in place: out[r,c] = -sum_k Linv_kk[r][k] S[r0+k][j0+c]
+        const int j0 = pt.y * TB;
+        gemm_accum<true, false>(acc, Li + (size_t)r0 * Mp + r0, Mp, Li + (size_t)r0 * Mp + j0, Mp, 0, TB, nullptr, sm);
         ACC_FOREACH(true, false, 0, 0, {
             *reinterpret_cast<double2*>(Li + (size_t)(r0 + row) * Mp + j0 + col) = make_double2(-v0, -v1);
         })
     }
 }
 
+// trailing update of block step kb over every lower tile (i, j) with i > kb
 __global__ void __launch_bounds__(GEMM_THREADS)
-k_chol_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, int kb, GpParams prm,
-             double* __restrict__ ws, double* __restrict__ scratch) {
-    extern __shared__ __align__(16) unsigned char smem_panel[];
-    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_panel);
-    const int2 pt = ptiles[blockIdx.x];
-    const Region R = regs[pt.x];
-    panel_tile(R, prm.D, kb, pt.y, ws, scratch + (size_t)blockIdx.x * TB * TB, sm);
-}
-
-// The whole blocked sweep (all block steps, all regions of a group) as ONE persistent launch: CTAs
-// draw (region, step, tile) tasks from a list sorted by step through an atomic ticket and wait on
-// per-(region, step) completion counters, so every region advances at its own pace and no SM idles
-// between steps.  A task only ever waits for tasks with a smaller ticket, which are running or done,
-// hence no deadlock however few CTAs are resident.  Counters grow by nb per (region, step) and sweep
-// ("epoch"), so they are never reset.
-__global__ void __launch_bounds__(GEMM_THREADS)
-k_chol_sweep(const Region* __restrict__ regs, const int4* __restrict__ tasks, int n_tasks, int nbmax,
-             int* __restrict__ done, int* __restrict__ ticket, int epoch, GpParams prm, double* __restrict__ ws,
-             double* __restrict__ scratch, int32_t* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem_sweep[];
-    __shared__ int s_task;
-    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_sweep);
-    double* tmp = scratch + (size_t)blockIdx.x * TB * TB;
-    const int tid = threadIdx.x;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_task = atomicAdd(ticket, 1);
-        __syncthreads();
-        const int task = s_task;
-        if (task >= n_tasks) break;
-        const int4 t = tasks[task];
-        const Region R = regs[t.x];
-        const int kb = t.y;
-        int* cnt = done + (size_t)t.x * nbmax + kb;
-        if (tid == 0) {
-            const volatile int* flag = nullptr;
-            int need = 0;
-            if (t.z < 0) {
-                if (kb > 0) {
-                    flag = cnt - 1;                 // step kb-1 of this region complete in this sweep
-                    need = epoch * R.nb;
-                }
-            } else {
-                flag = cnt;                         // this step's diagonal tile done
-                need = (epoch - 1) * R.nb + 1;
+k_rl_update(const Region* __restrict__ regs, const int4* __restrict__ tiles, int kb, GpParams prm,
+            double* __restrict__ ws) {
+    extern __shared__ __align__(16) unsigned char smem_upd[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_upd);
+    const int4 t = tiles[blockIdx.x];
+    const Region R = regs[t.x];
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
+    double* base = ws + R.base;
+    const int Mp = R.Mp;
+    double* Lg = base + lay.L;
+    double* Li = base + lay.Linv;
+    const int r0 = kb * TB, i0 = t.y * TB, j0 = t.z * TB;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    if (t.z > kb) {
+        // K[i,j] -= L[i,kb] L[j,kb]^T
+        gemm_accum<true, true>(acc, Lg + (size_t)i0 * Mp + r0, Mp, Lg + (size_t)j0 * Mp + r0, Mp, 0, TB, nullptr, sm);
+        ACC_FOREACH(true, true, 0, 0, {
+            double2* p = reinterpret_cast<double2*>(Lg + (size_t)(i0 + row) * Mp + j0 + col);
+            const double2 k = __ldcg(p);
+            *p = make_double2(k.x - v0, k.y - v1);
+        })
+    } else {
+        // S[i,j] (+)= L[i,kb] Linv[kb,j]
+        gemm_accum<true, false>(acc, Lg + (size_t)i0 * Mp + r0, Mp, Li + (size_t)r0 * Mp + j0, Mp, 0, TB, nullptr, sm);
+        const bool first = t.z == kb;
+        ACC_FOREACH(true, false, 0, 0, {
+            double2* p = reinterpret_cast<double2*>(Li + (size_t)(i0 + row) * Mp + j0 + col);
+            double2 o = make_double2(v0, v1);
+            if (!first) {
+                const double2 k = __ldcg(p);
+                o.x += k.x;
+                o.y += k.y;
             }
-            if (flag) {
-                while (*flag < need) __nanosleep(40);
-                __threadfence();
-            }
-        }
-        __syncthreads();
-        if (t.z < 0)
-            diag_step(R, prm.D, kb, ws, status, smem_sweep);
-        else
-            panel_tile(R, prm.D, kb, t.z, ws, tmp, sm);
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) atomicAdd(cnt, 1);
+            *p = o;
+        })
     }
 }
 
@@ -985,13 +952,9 @@ size_t region_doubles(const Region& r, int D) {
     return (size_t)gapro_align_up((size_t)make_layout(r.Mp, r.Np, r.Wp, D).total, 32);
 }
 
-// bytes of tables + descriptors + sweep state + panel scratch for a set of regions
-constexpr int SWEEP_MAX_GRID = 320;
-constexpr int SWEEP_TICKETS = 4096;
-
+// bytes of descriptors + tile tables for a set of regions
 size_t aux_bytes(const std::vector<Region>& rs) {
-    size_t full = 0, lower = 0, wide = 0, rows = 0, rowsp = 0, panel = 0;
-    int nbmax = 0;
+    size_t full = 0, lower = 0, wide = 0, rows = 0, rowsp = 0, panel = 0, upd = 0;
     for (const Region& r : rs) {
         full += (size_t)r.nb * r.nb;
         lower += (size_t)r.nb * (r.nb + 1) / 2;
@@ -999,17 +962,13 @@ size_t aux_bytes(const std::vector<Region>& rs) {
         rows += r.nb;
         rowsp += r.Np / TB;
         panel += r.nb - 1;
-        nbmax = std::max(nbmax, r.nb);
+        upd += (size_t)(r.nb - 1) * r.nb * (r.nb + 1) / 3;      // sum_kb sum_{i>kb} (i+1)
     }
-    const size_t scratch_tiles = std::max(panel, std::min(full, (size_t)SWEEP_MAX_GRID));
     size_t b = 0;
     b += gapro_align_up(rs.size() * sizeof(Region), 256);
     b += gapro_align_up(full * 16, 256) + gapro_align_up(lower * 16, 256) + gapro_align_up(wide * 16, 256);
     b += gapro_align_up(rows * 8, 256) + gapro_align_up(rowsp * 8, 256) + gapro_align_up(panel * 8, 256);
-    b += gapro_align_up(full * 16, 256);                                  // sweep task list
-    b += gapro_align_up(rs.size() * (size_t)nbmax * 4, 256);             // sweep completion counters
-    b += gapro_align_up((size_t)SWEEP_TICKETS * 4, 256);                  // sweep tickets
-    b += gapro_align_up(scratch_tiles * TB * TB * 8, 256);
+    b += gapro_align_up(upd * 16, 256);
     return b + 256 + (size_t)4 * 12 * 256;   // + per-group table alignment slack (MAX_GROUPS side streams)
 }
 
@@ -1019,11 +978,8 @@ struct ChunkTables {
     Region* regs;
     int4 *full, *lower, *wide;
     int2 *rows, *rowsp, *panel;
-    double* scratch;
-    int4* sweep_tasks;
-    int* sweep_done;
-    int* sweep_tickets;
-    int n_sweep, sweep_grid;
+    int4* upd;                      // update tiles of all block steps, step-major
+    std::vector<int> upd_off;       // upd_off[kb] .. upd_off[kb+1]: tiles of step kb
     int n_full, n_lower, n_wide, n_rows, n_rowsp;
     std::vector<int> cnt_gt;        // cnt_gt[kb] = #regions with nb > kb
     std::vector<int> panel_prefix;  // panel tiles of the first cnt_gt[kb] regions
@@ -1070,7 +1026,7 @@ void prof_account_train(const Region& r, int steps) {
         g_prof.flops_alg[ph] += steps * alg;
         g_prof.flops_exe[ph] += steps * exe;
     };
-    add(PH_CHOL, 2.0 * m3 / 3.0, t3 * (nb * (nb + 1) * (2 * nb + 1) / 6.0 + nb * (nb - 1) / 2.0 * 2 + nb * nb * nb / 3.0));
+    add(PH_CHOL, 2.0 * m3 / 3.0, t3 * (nb * (nb - 1) + (nb - 1) * nb * (nb + 1) / 3.0));
     add(PH_A, m3, kfull_tri);
     add(PH_B, m3, kfull_tri);
     add(PH_GA, m3, kfull_tri);
@@ -1091,8 +1047,6 @@ struct Driver {
     int n_regs;
     ChunkTables tb;
     PredictOut po;
-    int epoch = 0;
-    bool use_sweep = true;
 
     GpParams params(int step, int predict) const {
         GpParams p;
@@ -1125,22 +1079,19 @@ struct Driver {
     }
 
     void cholesky(const GpParams& p) {
-        if (use_sweep && epoch + 1 < SWEEP_TICKETS) {
-            ++epoch;
-            k_chol_sweep<<<tb.sweep_grid, GEMM_THREADS, DIAG_SMEM, stream>>>(tb.regs, tb.sweep_tasks, tb.n_sweep, tb.nbmax,
-                                                                           tb.sweep_done, tb.sweep_tickets + epoch, epoch,
-                                                                           p, ws, tb.scratch, po.status);
-            ++g_launches;
-            return;
-        }
         for (int kb = 0; kb < tb.nbmax; ++kb) {
             const int live = tb.cnt_gt[kb];
             if (live <= 0) break;
-            k_chol_diag<<<live, GEMM_THREADS, DIAG_SMEM, stream>>>(tb.regs, kb, p, ws, po.status);
+            k_rl_diag<<<live, GEMM_THREADS, DIAG_SMEM, stream>>>(tb.regs, kb, p, ws, po.status);
             ++g_launches;
             const int np = tb.panel_prefix[kb];
             if (np > 0) {
-                k_chol_panel<<<np, GEMM_THREADS, GEMM_SMEM, stream>>>(tb.regs, tb.panel, kb, p, ws, tb.scratch);
+                k_rl_panel<<<np, GEMM_THREADS, GEMM_SMEM, stream>>>(tb.regs, tb.panel, kb, p, ws);
+                ++g_launches;
+            }
+            const int nu = tb.upd_off[kb + 1] - tb.upd_off[kb];
+            if (nu > 0) {
+                k_rl_update<<<nu, GEMM_THREADS, GEMM_SMEM, stream>>>(tb.regs, tb.upd + tb.upd_off[kb], kb, p, ws);
                 ++g_launches;
             }
         }
@@ -1238,31 +1189,18 @@ int setup_chunk(std::vector<Region>& rs, char* aux, cudaStream_t stream, ChunkTa
     tb.rows = (int2*)put(rows.data(), rows.size() * 8);
     tb.rowsp = (int2*)put(rowsp.data(), rowsp.size() * 8);
     tb.panel = (int2*)put(panel.data(), panel.size() * 8);
-    // sweep tasks sorted by block step: all diagonal tiles of a step, then all its panel tiles
-    std::vector<int4> tasks;
-    tasks.reserve(full.size());
+    // update tiles, step-major: step kb touches every lower tile (i, j <= i) with i > kb
+    std::vector<int4> upd;
+    tb.upd_off.assign(tb.nbmax + 1, 0);
     for (int kb = 0; kb < tb.nbmax; ++kb) {
+        tb.upd_off[kb] = (int)upd.size();
         const int live = tb.cnt_gt[kb];
-        for (int r = 0; r < live; ++r) tasks.push_back(make_int4(r, kb, -1, 0));
         for (int r = 0; r < live; ++r)
-            for (int t = 0; t < rs[r].nb - 1; ++t) tasks.push_back(make_int4(r, kb, t, 0));
+            for (int i = rs[r].nb - 1; i > kb; --i)
+                for (int j = 0; j <= i; ++j) upd.push_back(make_int4(r, i, j, 0));
     }
-    tb.sweep_tasks = (int4*)put(tasks.data(), tasks.size() * 16);
-    tb.n_sweep = (int)tasks.size();
-    tb.sweep_done = (int*)(aux + o);
-    {
-        const size_t bytes = gapro_align_up(rs.size() * (size_t)tb.nbmax * 4, 256);
-        cudaMemsetAsync(aux + o, 0, bytes, stream);
-        o += bytes;
-    }
-    tb.sweep_tickets = (int*)(aux + o);
-    {
-        const size_t bytes = gapro_align_up((size_t)SWEEP_TICKETS * 4, 256);
-        cudaMemsetAsync(aux + o, 0, bytes, stream);
-        o += bytes;
-    }
-    tb.sweep_grid = std::min(tb.n_sweep, SWEEP_MAX_GRID);
-    tb.scratch = (double*)(aux + o);
+    tb.upd_off[tb.nbmax] = (int)upd.size();
+    tb.upd = (int4*)put(upd.data(), upd.size() * 16);
     tb.n_full = (int)full.size();
     tb.n_lower = (int)lower.size();
     tb.n_wide = (int)wide.size();
@@ -1359,9 +1297,9 @@ static int set_kernel_attributes() {
     static bool done = false;
     if (done) return GAPRO_OK;
     int rc = allow_smem(k_build, 3 * TB * 64 * 8);
-    if (rc == GAPRO_OK) rc = allow_smem(k_chol_diag, DIAG_SMEM);
-    if (rc == GAPRO_OK) rc = allow_smem(k_chol_panel, GEMM_SMEM);
-    if (rc == GAPRO_OK) rc = allow_smem(k_chol_sweep, DIAG_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_rl_diag, DIAG_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_rl_panel, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_rl_update, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_A>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_B>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GA>, GEMM_SMEM);
@@ -1422,7 +1360,6 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             d.ws = (double*)ws;
             d.n_regs = (int)groups[g].size();
             d.po = po;
-            if (const char* e = getenv("GAPRO_CHOL_SWEEP")) d.use_sweep = atoi(e) != 0;
             rc = setup_chunk(groups[g], aux, stream, d.tb);     // uploads on the caller's stream, then syncs
             if (rc != GAPRO_OK) return rc;
             aux += aux_bytes(groups[g]);

@@ -317,6 +317,18 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// scene of global superpoint g: one coalesced load of the offsets + a ballot instead of a chain of
+// dependent binary-search loads
+__device__ __forceinline__ int warp_find_scene(const int32_t* __restrict__ spp_off, int n_scenes, int g, int lane) {
+    int sc = -1;
+    for (int base = 0; base <= n_scenes; base += 32) {
+        const int i = base + lane;
+        const bool le = (i <= n_scenes) && (spp_off[i] <= g);
+        sc += __popc(__ballot_sync(FULL_MASK, le));
+    }
+    return sc;
+}
+
 template <int WORDS>
 __global__ void __launch_bounds__(256)
 k_occupancy(const double* __restrict__ xyz, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
@@ -327,11 +339,11 @@ k_occupancy(const double* __restrict__ xyz, const int32_t* __restrict__ perm, co
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= s_total) return;
-    const int sc = gapro_find_segment<int32_t>(spp_off, n_scenes, g);
-    const int b0 = box_off[sc];
-    const int nb = box_off[sc + 1] - b0;
     const int start = seg_off[g], end = seg_off[g + 1];
     const int cnt = end - start;
+    const int sc = warp_find_scene(spp_off, n_scenes, g, lane);
+    const int b0 = box_off[sc];
+    const int nb = box_off[sc + 1] - b0;
 
     // pass 1: extent of the superpoint; the first 32 points stay in registers
     double px = 0, py = 0, pz = 0;
@@ -463,51 +475,50 @@ extern "C" int gapro_occupancy(const double* xyz, const int32_t* perm, const int
 // =============================================================================================
 // B — feature pooling (gen_ps_utils.py:357): float32 sum in point-index order, / float32 count
 // =============================================================================================
-// One warp per superpoint.  Lane (p, d) gathers feature d of point p of the current group of
-// P = 32 / D points (several independent gathers in flight per superpoint); the float32 adds are
-// then replayed strictly in point order through warp shuffles, so the sum is the index-ordered
-// float32 sum of torch_scatter's CPU kernel, bit for bit.
-__global__ void __launch_bounds__(256)
+// One warp per superpoint.  For every chunk of 32 points the warp loads the point indices with one
+// coalesced read, issues all D*32 feature gathers at once (independent loads, one memory latency),
+// stages them in shared memory, and lanes d < D then replay the float32 adds strictly in point
+// order — the index-ordered float32 sum of torch_scatter's CPU kernel, bit for bit.
+constexpr int POOL_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * POOL_WARPS)
 k_pool_feats(const float* __restrict__ feats, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
              int s_total, int D, float* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    extern __shared__ float pool_smem[];               // [POOL_WARPS][32 * D]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x * POOL_WARPS + warp;
     if (g >= s_total) return;
+    float* stage = pool_smem + (size_t)warp * 32 * D;
     const int start = seg_off[g], end = seg_off[g + 1];
-    const float fcnt = (float)(end - start);
-    if (D <= 16) {
-        const int P = 32 / D;
-        const int p = lane / D, d = lane - p * D;
-        const bool worker = p < P;
-        float acc = 0.0f;
-        for (int base = start; base < end; base += 2 * P) {
-            // two groups of P points in flight
-            const int k0 = base + p, k1 = base + P + p;
-            float v0 = 0.0f, v1 = 0.0f;
-            if (worker && k0 < end) v0 = feats[(int64_t)perm[k0] * D + d];
-            if (worker && k1 < end) v1 = feats[(int64_t)perm[k1] * D + d];
-            const int n0 = min(P, end - base), n1 = min(P, max(end - base - P, 0));
-            for (int q = 0; q < n0; ++q) acc = __fadd_rn(acc, __shfl_sync(FULL_MASK, v0, q * D + d));
-            for (int q = 0; q < n1; ++q) acc = __fadd_rn(acc, __shfl_sync(FULL_MASK, v1, q * D + d));
+    float acc[2] = {0.0f, 0.0f};                       // lane handles dims lane and lane + 32 (D <= 64)
+    for (int base = start; base < end; base += 32) {
+        const int n = min(32, end - base);
+        const int myp = (lane < n) ? perm[base + lane] : 0;
+        const int total = n * D;
+        for (int e0 = 0; e0 < total; e0 += 32) {           // warp-uniform trip count (full-mask shuffles)
+            const int e = e0 + lane;
+            const int ec = min(e, total - 1);
+            const int pt = ec / D, d = ec - pt * D;
+            const int p = __shfl_sync(FULL_MASK, myp, pt);
+            if (e < total) stage[e] = feats[(int64_t)p * D + d];
         }
-        if (lane < D) out[(int64_t)g * D + d] = __fdiv_rn(acc, fcnt);
-    } else {
-        for (int d = lane; d < D; d += 32) {
-            float acc = 0.0f;
-            int k = start;
-            for (; k + 4 <= end; k += 4) {     // four independent gathers in flight, adds strictly in order
-                const float v0 = feats[(int64_t)perm[k] * D + d];
-                const float v1 = feats[(int64_t)perm[k + 1] * D + d];
-                const float v2 = feats[(int64_t)perm[k + 2] * D + d];
-                const float v3 = feats[(int64_t)perm[k + 3] * D + d];
-                acc = __fadd_rn(acc, v0);
-                acc = __fadd_rn(acc, v1);
-                acc = __fadd_rn(acc, v2);
-                acc = __fadd_rn(acc, v3);
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int d = lane + 32 * h;
+            if (d < D) {
+                float a = acc[h];
+                for (int pt = 0; pt < n; ++pt) a = __fadd_rn(a, stage[pt * D + d]);
+                acc[h] = a;
             }
-            for (; k < end; ++k) acc = __fadd_rn(acc, feats[(int64_t)perm[k] * D + d]);
-            out[(int64_t)g * D + d] = __fdiv_rn(acc, fcnt);
         }
+        __syncwarp();
+    }
+    const float fcnt = (float)(end - start);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int d = lane + 32 * h;
+        if (d < D) out[(int64_t)g * D + d] = __fdiv_rn(acc[h], fcnt);
     }
 }
 
@@ -516,7 +527,17 @@ extern "C" int gapro_pool_feats(const float* feats, const int32_t* perm, const i
     cudaStream_t stream = (cudaStream_t)stream_;
     GAPRO_REQUIRE(feats && perm && seg_off && out, "gapro_pool_feats: null pointer");
     GAPRO_REQUIRE(s_total > 0 && D > 0, "gapro_pool_feats: empty input");
-    k_pool_feats<<<(unsigned)((s_total + 7) / 8), 256, 0, stream>>>(feats, perm, seg_off, s_total, D, out);
+    GAPRO_REQUIRE(D <= 64, "gapro_pool_feats: feature dimension %d > 64", D);
+    const size_t smem = (size_t)POOL_WARPS * 32 * D * sizeof(float);
+    if (smem > 48 * 1024) {
+        static bool attr = false;
+        if (!attr) {
+            GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_pool_feats, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            attr = true;
+        }
+    }
+    k_pool_feats<<<(unsigned)((s_total + POOL_WARPS - 1) / POOL_WARPS), 32 * POOL_WARPS, smem, stream>>>(
+        feats, perm, seg_off, s_total, D, out);
     GAPRO_KERNEL_CHECK();
     return GAPRO_OK;
 }

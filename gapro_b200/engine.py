@@ -87,7 +87,7 @@ class GaproEngine:
     # ------------------------------------------------------------------ main entry
     def run(self, scenes: Sequence[SceneInputs], instance_classes=18, ground_h=0.1, training_iter=50,
             thresh_spp_occu=0.8, jitter_zz=1e-4, jitter_xx=1e-4, lr=0.1, debug: bool = False,
-            want_cnt_in: bool = False, keep: bool = False):
+            want_cnt_in: bool = False, keep: bool = False, stages_only: bool = False):
         """Returns a list of (sem[N] i32, inst[N] i32, prob[N] f32, mu[S] f32, var[S] f32) device
         tensors, one tuple per scene — the return of gen_pseudo_label_gaussian_process
         (/root/reference/gapro/gen_ps_utils.py:482) — plus a BatchDebug when debug=True."""
@@ -180,6 +180,17 @@ class GaproEngine:
         _lib.check(lib.gapro_pool_feats(feats.data_ptr(), perm.data_ptr(), seg_off.data_ptr(), St, D,
                                         feats_spp.data_ptr(), stream), "gapro_pool_feats")
         n_launch += 1
+
+        if stages_only:      # benchmarking hook: stop after the memory-bound stages, keep their buffers
+            self.last = dict(xyz=xyz, feats=feats, perm=perm, seg_off=seg_off, spp_gid=spp_gid, spp_off_dev=spp_off_dev,
+                             box_off_dev=box_off_dev, boxes=boxes, occ_bits=occ_bits, n_bbs=n_bbs, excl_cnt=excl_cnt,
+                             inter_cnt=inter_cnt, feats_spp=feats_spp,
+                             packed_spp=torch.zeros((St, 4), dtype=torch.int32, device=dev),
+                             sem=torch.empty(N, dtype=torch.int32, device=dev),
+                             inst=torch.empty(N, dtype=torch.int32, device=dev),
+                             prob=torch.empty(N, dtype=torch.float32, device=dev), ns=ns, St=St, Bt=Bt, N=N, D=D,
+                             words=words, thresh=float(np.float32(thresh_spp_occu)))
+            return None
 
         # ---- P: pair state machine on the host --------------------------------------------
         boxes_h = boxes.cpu().numpy()

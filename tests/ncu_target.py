@@ -15,7 +15,11 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev = torch.device("cuda:0")
 eng = get_engine(dev)
-scenes = [to_scene_inputs(synthetic_inputs(synthetic.make_scene(100 + i, cfg)), dev, noise_seed=i) for i in range(n)]
+def _cfg(i):
+    return synthetic.c3_config(i) if cfg == "c3" else cfg
+
+
+scenes = [to_scene_inputs(synthetic_inputs(synthetic.make_scene(1000 + i, _cfg(i))), dev, noise_seed=i) for i in range(n)]
 eng.run(scenes, thresh_spp_occu=0.999, training_iter=iters)
 torch.cuda.synchronize()
 print("done", eng.last_stats["n_regions"], eng.last_stats["launches"])
