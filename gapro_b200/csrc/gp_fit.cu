@@ -1047,6 +1047,8 @@ struct Driver {
     int n_regs;
     ChunkTables tb;
     PredictOut po;
+    cudaEvent_t ev_wait = nullptr;     // stagger: start the first step after the previous group's first sweep
+    cudaEvent_t ev_signal = nullptr;   // ... and tell the next group when ours is done
 
     GpParams params(int step, int predict) const {
         GpParams p;
@@ -1117,8 +1119,10 @@ struct Driver {
     X;                               \
     prof_end(stream);                \
     ++ph;
+        if (step == 1 && ev_wait) cudaStreamWaitEvent(stream, ev_wait, 0);
         PHASE(build(p))
         PHASE(cholesky(p))
+        if (step == 1 && ev_signal) cudaEventRecord(ev_signal, stream);
         PHASE(gemm<PH_A>(tb.full, tb.n_full, p))
         PHASE(gemm<PH_B>(tb.full, tb.n_full, p))
         PHASE((k_colstats<<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws, po), ++g_launches))
@@ -1262,6 +1266,7 @@ constexpr int MAX_GROUPS = 4;
 struct StreamPool {
     cudaStream_t s[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork = nullptr, join[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stagger[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
     bool ready = false;
 };
 thread_local StreamPool g_pool;
@@ -1271,6 +1276,7 @@ static int ensure_pool() {
     for (int i = 0; i < MAX_GROUPS; ++i) {
         GAPRO_CUDA_TRY(cudaStreamCreateWithFlags(&g_pool.s[i], cudaStreamNonBlocking));
         GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.join[i], cudaEventDisableTiming));
+        GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.stagger[i], cudaEventDisableTiming));
     }
     GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.fork, cudaEventDisableTiming));
     g_pool.ready = true;
@@ -1360,6 +1366,12 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             d.ws = (double*)ws;
             d.n_regs = (int)groups[g].size();
             d.po = po;
+            if (G > 1 && iters > 0 && !getenv("GAPRO_GP_NO_STAGGER")) {
+                // groups run the same phase sequence; offsetting them by one sweep keeps one group's
+                // latency-bound block chain under the other groups' tile products
+                d.ev_signal = g + 1 < G ? g_pool.stagger[g] : nullptr;
+                d.ev_wait = g > 0 ? g_pool.stagger[g - 1] : nullptr;
+            }
             rc = setup_chunk(groups[g], aux, stream, d.tb);     // uploads on the caller's stream, then syncs
             if (rc != GAPRO_OK) return rc;
             aux += aux_bytes(groups[g]);
