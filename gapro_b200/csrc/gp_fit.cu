@@ -626,7 +626,12 @@ k_rl_update(const Region* __restrict__ regs, const int4* __restrict__ tiles, int
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     if (t.z > kb) {
-        // K[i,j] -= L[i,kb] L[j,kb]^T
+        // K[i,j] -= L[i,kb] L[j,kb]^T   (pull the read-modify-write tile towards L2 while the product runs)
+        ACC_FOREACH(true, true, 0, 0, {
+            (void)v0;
+            (void)v1;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Lg + (size_t)(i0 + row) * Mp + j0 + col));
+        })
         gemm_accum<true, true>(acc, Lg + (size_t)i0 * Mp + r0, Mp, Lg + (size_t)j0 * Mp + r0, Mp, 0, TB, nullptr, sm);
         ACC_FOREACH(true, true, 0, 0, {
             double2* p = reinterpret_cast<double2*>(Lg + (size_t)(i0 + row) * Mp + j0 + col);
@@ -635,8 +640,15 @@ k_rl_update(const Region* __restrict__ regs, const int4* __restrict__ tiles, int
         })
     } else {
         // S[i,j] (+)= L[i,kb] Linv[kb,j]
-        gemm_accum<true, false>(acc, Lg + (size_t)i0 * Mp + r0, Mp, Li + (size_t)r0 * Mp + j0, Mp, 0, TB, nullptr, sm);
         const bool first = t.z == kb;
+        if (!first) {
+            ACC_FOREACH(true, false, 0, 0, {
+                (void)v0;
+                (void)v1;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(Li + (size_t)(i0 + row) * Mp + j0 + col));
+            })
+        }
+        gemm_accum<true, false>(acc, Lg + (size_t)i0 * Mp + r0, Mp, Li + (size_t)r0 * Mp + j0, Mp, 0, TB, nullptr, sm);
         ACC_FOREACH(true, false, 0, 0, {
             double2* p = reinterpret_cast<double2*>(Li + (size_t)(i0 + row) * Mp + j0 + col);
             double2 o = make_double2(v0, v1);
@@ -1047,8 +1059,26 @@ struct Driver {
     int n_regs;
     ChunkTables tb;
     PredictOut po;
-    cudaEvent_t ev_wait = nullptr;     // stagger: start the first step after the previous group's first sweep
-    cudaEvent_t ev_signal = nullptr;   // ... and tell the next group when ours is done
+    // two-priority scheme: the latency-bound part of a step (kernel matrices + block sweep) runs on a
+    // high-priority stream, the throughput-bound tile products on a low-priority one, so that the block
+    // chain of one group is scheduled ahead of the other groups' tile products instead of behind them
+    cudaStream_t s_hi = nullptr, s_lo = nullptr;
+    cudaEvent_t ev_swept = nullptr, ev_stepped = nullptr;
+
+    void to_hi() {
+        if (!s_hi) return;
+        cudaStreamWaitEvent(s_hi, ev_stepped, 0);      // (a never-recorded event is complete)
+        stream = s_hi;
+    }
+    void to_lo() {
+        if (!s_hi) return;
+        cudaEventRecord(ev_swept, s_hi);
+        cudaStreamWaitEvent(s_lo, ev_swept, 0);
+        stream = s_lo;
+    }
+    void step_done() {
+        if (s_hi) cudaEventRecord(ev_stepped, s_lo);
+    }
 
     GpParams params(int step, int predict) const {
         GpParams p;
@@ -1119,10 +1149,10 @@ struct Driver {
     X;                               \
     prof_end(stream);                \
     ++ph;
-        if (step == 1 && ev_wait) cudaStreamWaitEvent(stream, ev_wait, 0);
+        to_hi();
         PHASE(build(p))
         PHASE(cholesky(p))
-        if (step == 1 && ev_signal) cudaEventRecord(ev_signal, stream);
+        to_lo();
         PHASE(gemm<PH_A>(tb.full, tb.n_full, p))
         PHASE(gemm<PH_B>(tb.full, tb.n_full, p))
         PHASE((k_colstats<<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws, po), ++g_launches))
@@ -1137,13 +1167,16 @@ struct Driver {
         PHASE(kgrad(p))
         PHASE((k_adam_small<<<n_regs, 256, 0, stream>>>(tb.regs, p, ws), ++g_launches))
 #undef PHASE
+        step_done();
     }
 
     void predict() {
         const GpParams p = params(0, 1);
         prof_begin(PROF_PREDICT, stream);
+        to_hi();
         build(p);
         cholesky(p);
+        to_lo();
         gemm<PH_A>(tb.wide, tb.n_wide, p);
         gemm<PH_B>(tb.wide, tb.n_wide, p);
         if (tb.n_rowsp > 0) {
@@ -1264,19 +1297,25 @@ extern "C" int64_t gapro_gp_last_launch_count(void) { return g_launches; }
 // Cholesky sweep of one group overlaps the tile products of the others --------------------------------
 constexpr int MAX_GROUPS = 4;
 struct StreamPool {
-    cudaStream_t s[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t hi[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t lo[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork = nullptr, join[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t stagger[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t swept[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stepped[MAX_GROUPS] = {nullptr, nullptr, nullptr, nullptr};
     bool ready = false;
 };
 thread_local StreamPool g_pool;
 
 static int ensure_pool() {
     if (g_pool.ready) return GAPRO_OK;
+    int least = 0, greatest = 0;
+    GAPRO_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     for (int i = 0; i < MAX_GROUPS; ++i) {
-        GAPRO_CUDA_TRY(cudaStreamCreateWithFlags(&g_pool.s[i], cudaStreamNonBlocking));
+        GAPRO_CUDA_TRY(cudaStreamCreateWithPriority(&g_pool.hi[i], cudaStreamNonBlocking, greatest));
+        GAPRO_CUDA_TRY(cudaStreamCreateWithPriority(&g_pool.lo[i], cudaStreamNonBlocking, least));
         GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.join[i], cudaEventDisableTiming));
-        GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.stagger[i], cudaEventDisableTiming));
+        GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.swept[i], cudaEventDisableTiming));
+        GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.stepped[i], cudaEventDisableTiming));
     }
     GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.fork, cudaEventDisableTiming));
     g_pool.ready = true;
@@ -1358,7 +1397,14 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
         char* aux = (char*)ws + doubles * 8;
         for (int g = 0; g < G; ++g) {
             Driver& d = drv[g];
-            d.stream = G > 1 ? g_pool.s[g] : stream;
+            d.stream = stream;
+            if (G > 1) {
+                d.s_hi = g_pool.hi[g];
+                d.s_lo = g_pool.lo[g];
+                d.ev_swept = g_pool.swept[g];
+                d.ev_stepped = g_pool.stepped[g];
+                d.stream = d.s_hi;
+            }
             d.D = D;
             d.lr = lr;
             d.jitter_zz = jitter_zz;
@@ -1366,19 +1412,18 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             d.ws = (double*)ws;
             d.n_regs = (int)groups[g].size();
             d.po = po;
-            if (G > 1 && iters > 0 && !getenv("GAPRO_GP_NO_STAGGER")) {
-                // groups run the same phase sequence; offsetting them by one sweep keeps one group's
-                // latency-bound block chain under the other groups' tile products
-                d.ev_signal = g + 1 < G ? g_pool.stagger[g] : nullptr;
-                d.ev_wait = g > 0 ? g_pool.stagger[g - 1] : nullptr;
-            }
             rc = setup_chunk(groups[g], aux, stream, d.tb);     // uploads on the caller's stream, then syncs
             if (rc != GAPRO_OK) return rc;
             aux += aux_bytes(groups[g]);
         }
         if (G > 1) {
             GAPRO_CUDA_TRY(cudaEventRecord(g_pool.fork, stream));
-            for (int g = 0; g < G; ++g) GAPRO_CUDA_TRY(cudaStreamWaitEvent(drv[g].stream, g_pool.fork, 0));
+            for (int g = 0; g < G; ++g) {
+                GAPRO_CUDA_TRY(cudaStreamWaitEvent(drv[g].s_hi, g_pool.fork, 0));
+                GAPRO_CUDA_TRY(cudaStreamWaitEvent(drv[g].s_lo, g_pool.fork, 0));
+                // a fresh "previous step finished" marker, so that the first to_hi() does not wait on a stale one
+                GAPRO_CUDA_TRY(cudaEventRecord(drv[g].ev_stepped, drv[g].s_lo));
+            }
         }
         for (int g = 0; g < G; ++g) {
             k_region_init<<<drv[g].n_regs, 256, 0, drv[g].stream>>>(drv[g].tb.regs, D, feats_spp, train_idx, test_idx,
@@ -1395,7 +1440,10 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             for (int g = 0; g < G; ++g) drv[g].predict();
         if (G > 1)
             for (int g = 0; g < G; ++g) {
-                GAPRO_CUDA_TRY(cudaEventRecord(g_pool.join[g], drv[g].stream));
+                // whatever ran last on either stream of the group must be done
+                GAPRO_CUDA_TRY(cudaEventRecord(g_pool.join[g], drv[g].s_hi));
+                GAPRO_CUDA_TRY(cudaStreamWaitEvent(drv[g].s_lo, g_pool.join[g], 0));
+                GAPRO_CUDA_TRY(cudaEventRecord(g_pool.join[g], drv[g].s_lo));
                 GAPRO_CUDA_TRY(cudaStreamWaitEvent(stream, g_pool.join[g], 0));
             }
         GAPRO_KERNEL_CHECK();
