@@ -24,11 +24,11 @@ def gp_debug_state(feats_spp, train_idx, n_b1, test_idx, init_noise, iters=0, st
     toff = np.array([0, N], dtype=np.int32)
     nbytes = lib.gapro_gp_workspace_bytes(1, off.ctypes.data, toff.ctypes.data, D) + 4096
     ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-    layout = np.zeros(31, dtype=np.int64)
+    layout = np.zeros(32, dtype=np.int64)
     stream = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(lib.gapro_gp_debug_run(feats.data_ptr(), D, M, int(n_b1), N, tr.data_ptr(), te.data_ptr(), nz.data_ptr(),
                                       int(iters), int(stop_phase), float(lr), float(jitter_zz), float(jitter_xx),
-                                      ws.data_ptr(), ws.numel(), layout.ctypes.data, 31, stream), "gapro_gp_debug_run")
+                                      ws.data_ptr(), ws.numel(), layout.ctypes.data, 32, stream), "gapro_gp_debug_run")
     torch.cuda.synchronize(dev)
     names = lib.gapro_gp_debug_layout_names().decode().split(",")
     lay = dict(zip(names, layout.tolist()))

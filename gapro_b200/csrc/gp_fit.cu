@@ -63,7 +63,7 @@ struct Region {
 
 struct Layout {
     long long X, Z, Zm, Zv, gZ, Xt, y, m, mm, mv, scal, mu, var, gmu, gv, gsrow, glrow;
-    long long L, Linv, T, Tm, Tv, GA, GC, Kzx, A, Bm, total;
+    long long L, Linv, T, Tm, Tv, GA, GC, Kc, Kzx, A, Bm, total;
 };
 enum { SC_C = 0, SC_RS = 1, SC_RL = 2, SC_M0 = 3, SC_V0 = 6, SC_N = 16 };
 
@@ -98,6 +98,7 @@ __host__ __device__ inline Layout make_layout(int Mp, int Np, int Wp, int D) {
     l.Tv = o; o += mm;
     l.GA = o; o += mm;
     l.GC = o; o += mm;
+    l.Kc = o; o += mm;
     l.Kzx = o; o += mw;
     l.A = o; o += mw;
     l.Bm = o; o += mw;
@@ -227,6 +228,12 @@ __device__ __forceinline__ void gemm_accum(double (&acc)[4][4][2], const double*
     }
     int stage = 0;
     for (int c = 0; c < nchunk; ++c) {
+        double2 sc0 = make_double2(1.0, 1.0), sc1 = sc0;
+        if (kscale) {                  // issued ahead of the barrier so the global latency is hidden
+            const double2* kp = reinterpret_cast<const double2*>(kscale + k0 + c * BK + 4 * tig);
+            sc0 = __ldg(kp);
+            sc1 = __ldg(kp + 1);
+        }
         cp_async_wait<NSTAGE - 2>();   // chunk c has landed
         __syncthreads();               // ... for every thread, and chunk c-1 is fully consumed
         {
@@ -248,7 +255,7 @@ __device__ __forceinline__ void gemm_accum(double (&acc)[4][4][2], const double*
             load_frags<AKC>(af, sa, wm32, gid, tig, h);
             load_frags<BKC>(bf, sb, wn32, gid, tig, h);
             if (kscale) {
-                const double2 sc = *reinterpret_cast<const double2*>(kscale + k0 + c * BK + 4 * tig + 2 * h);
+                const double2 sc = h ? sc1 : sc0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     af[i][0] *= sc.x;
@@ -292,7 +299,7 @@ enum Phase {
 };
 
 template <int PH>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 4)
 k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams prm, double* __restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_gemm[];
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_gemm);
@@ -366,30 +373,25 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
         gemm_accum<false, false>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, kend, nullptr, sm, mlim, nlim);
         double* out = base + lay.GC;
         ACC_FOREACH(false, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = make_double2(v0, v1); })
-    } else if (PH == PH_GL) {  // G_L = -tril(G_C A^T)   (into the G_A buffer)
-        gemm_accum<true, true>(acc, base + lay.GC + (size_t)r0 * Mp, Mp, base + lay.A + (size_t)c0 * Wp, Wp, 0, kend,
+    } else if (PH == PH_GL) {
+        // Cholesky adjoint without forming G_L: with Q = G_A A^T,
+        //   dLoss/dK_zz = -Linv^T sym(Phi(Q)) Linv,   sym(Phi(Q)) = 1/2 tril(Q) mirrored
+        // (from dA = -Phi(L^-1 dK L^-T) A; identical to L^-T sym(Phi(L^T G_L)) L^-1 with G_L = -tril(L^-T Q)).
+        // This phase writes S = -sym(Phi(Q)) into the B buffer.
+        gemm_accum<true, true>(acc, base + lay.GA + (size_t)r0 * Mp, Mp, base + lay.A + (size_t)c0 * Wp, Wp, 0, kend,
                                nullptr, sm, mlim, nlim);
-        double* out = base + lay.GA;
-        ACC_FOREACH(true, true, r0, c0, {
-            double2 o;
-            o.x = (col <= row) ? -v0 : 0.0;
-            o.y = (col + 1 <= row) ? -v1 : 0.0;
-            *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = o;
-        })
-    } else if (PH == PH_SP) {  // symP = 1/2 (P + P^T), P = Phi(L^T G_L): both = 1/2 tril(L^T G_L) mirrored
-        gemm_accum<false, false>(acc, base + lay.L + r0, Mp, base + lay.GA + c0, Mp, r0, kend, nullptr, sm, mlim, nlim);
         double* out = base + lay.Bm;
-        ACC_FOREACH(false, false, r0, c0, {
+        ACC_FOREACH(true, true, r0, c0, {
             _Pragma("unroll") for (int e = 0; e < 2; ++e) {
                 const int cc = col + e;
-                const double v = 0.5 * (e ? v1 : v0);
+                const double v = -0.5 * (e ? v1 : v0);
                 if (cc <= row) {
                     out[(size_t)row * Wp + cc] = v;
                     if (cc < row) out[(size_t)cc * Wp + row] = v;
                 }
             }
         })
-    } else if (PH == PH_Y) {   // Y = symP * Linv: k >= j   (into the G_A buffer)
+    } else if (PH == PH_Y) {   // Y = S * Linv: k >= j   (into the G_A buffer)
         gemm_accum<true, false>(acc, base + lay.Bm + (size_t)r0 * Wp, Wp, base + lay.Linv + c0, Mp, c0, kend, nullptr,
                                 sm, mlim, nlim);
         double* out = base + lay.GA;
@@ -440,6 +442,7 @@ k_build(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParam
     const double inv_l2 = 1.0 / (ell * ell);
     double* Kzx = base + lay.Kzx;
     double* Kzz = base + lay.L;
+    double* Kc = base + lay.Kc;
     for (int e = threadIdx.x; e < TB * TB; e += blockDim.x) {
         const int li = e >> 6, lj = e & 63;
         const int i = ti * TB + li, j = tj * TB + lj;
@@ -455,12 +458,16 @@ k_build(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParam
                 const double df = zi[li * D + d] - zj[lj * D + d];
                 q2 += df * df;
             }
-            double v;
-            if (i < R.M && j < R.M)
-                v = s * exp(-0.5 * (q2 * inv_l2)) + (i == j ? prm.jitter_zz : 0.0);
-            else
+            double v, v0 = 0.0;
+            if (i < R.M && j < R.M) {
+                v0 = s * exp(-0.5 * (q2 * inv_l2));
+                v = v0 + (i == j ? prm.jitter_zz : 0.0);
+            } else {
                 v = (i == j) ? 1.0 : 0.0;
+            }
             Kzz[(size_t)i * R.Mp + j] = v;
+            Kc[(size_t)i * R.Mp + j] = v0;            // jitter-free copy (both halves) for the gradient kernel
+            if (ti != tj) Kc[(size_t)j * R.Mp + i] = v0;
         }
     }
 }
@@ -571,7 +578,7 @@ k_rl_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __restr
     }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 4)
 k_rl_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, int kb, GpParams prm,
            double* __restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_panel[];
@@ -607,7 +614,7 @@ k_rl_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, int
 }
 
 // trailing update of block step kb over every lower tile (i, j) with i > kb
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 4)
 k_rl_update(const Region* __restrict__ regs, const int4* __restrict__ tiles, int kb, GpParams prm,
             double* __restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_upd[];
@@ -807,8 +814,9 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
         const double* GK = base + lay.Bm + (size_t)i * R.Wp;
         const double* GC = base + lay.GC + (size_t)i * R.Mp;
         const double* Kx = base + lay.Kzx + (size_t)i * R.Wp;
+        const double* Kcr = base + lay.Kc + (size_t)i * R.Mp;
         for (int j = lane; j < R.M; j += 32) {
-            // zz part: W = Gr + Gr^T = 2 Gr (G_K and K_zz symmetric)
+            // zz part: W = Gr + Gr^T = 2 Gr (G_K and K_zz symmetric); K_zz comes from the build phase
             const double* zj = Z + (size_t)j * D;
             double d2 = 0.0;
 #pragma unroll
@@ -817,10 +825,10 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
                 d2 += df * df;
             }
             double r2 = d2 * inv_l2;
-            const double E = exp(-0.5 * r2);
+            const double Kz = Kcr[j];
             double G = GK[j];
-            double Gr = -0.5 * G * (s * E);
-            as += G * E;
+            double Gr = -0.5 * G * Kz;
+            as += G * (Kz / s);
             al += Gr * (-2.0 * r2 / ell);
 #pragma unroll
             for (int d = 0; d < DMAX; ++d)
@@ -1045,7 +1053,6 @@ void prof_account_train(const Region& r, int steps) {
     add(PH_GT, m3, t3 * tri * nb);
     add(PH_GC, m3, kfull_tri);
     add(PH_GL, m3, t3 * tri * nb);
-    add(PH_SP, m3 / 3.0, t3 * nb * (nb + 1) * (nb + 2) / 6.0);
     add(PH_Y, m3, kfull_tri);
     add(PH_GK, m3 / 3.0, t3 * nb * (nb + 1) * (nb + 2) / 6.0);
     (void)Mp;
@@ -1161,7 +1168,7 @@ struct Driver {
         PHASE((k_grad_m<<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws), ++g_launches))
         PHASE(gemm<PH_GC>(tb.full, tb.n_full, p))
         PHASE(gemm<PH_GL>(tb.lower, tb.n_lower, p))
-        PHASE(gemm<PH_SP>(tb.lower, tb.n_lower, p))
+        PHASE((void)0)   // (slot of the former L^T G_L product, folded into the previous phase)
         PHASE(gemm<PH_Y>(tb.full, tb.n_full, p))
         PHASE(gemm<PH_GK>(tb.lower, tb.n_lower, p))
         PHASE(kgrad(p))
@@ -1334,7 +1341,11 @@ static int n_groups_for(size_t n_regions) {
 
 template <typename K>
 static int allow_smem(K kernel, int bytes) {
-    GAPRO_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    if (bytes > 0) GAPRO_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    // one shared-memory carve-out for every kernel of the stage: CTAs of kernels running concurrently on
+    // different streams can then be co-resident on an SM
+    GAPRO_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        (int)cudaSharedmemCarveoutMaxShared));
     return GAPRO_OK;
 }
 
@@ -1351,7 +1362,6 @@ static int set_kernel_attributes() {
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GT>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GC>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GL>, GEMM_SMEM);
-    if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_SP>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_Y>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GK>, GEMM_SMEM);
     done = rc == GAPRO_OK;
@@ -1569,7 +1579,7 @@ extern "C" int gapro_fp64_peak(int use_dmma, int iters, double* tflops, double* 
 }
 
 extern "C" const char* gapro_gp_debug_layout_names(void) {
-    return "X,Z,Zm,Zv,gZ,Xt,y,m,mm,mv,scal,mu,var,gmu,gv,gsrow,glrow,L,Linv,T,Tm,Tv,GA,GC,Kzx,A,Bm,total,Mp,Np,Wp";
+    return "X,Z,Zm,Zv,gZ,Xt,y,m,mm,mv,scal,mu,var,gmu,gv,gsrow,glrow,L,Linv,T,Tm,Tv,GA,GC,Kzx,A,Bm,total,Mp,Np,Wp,Kc";
 }
 
 extern "C" int gapro_gp_debug_run(const float* feats_spp, int32_t D, int32_t M, int32_t n_b1, int32_t N,
@@ -1579,13 +1589,13 @@ extern "C" int gapro_gp_debug_run(const float* feats_spp, int32_t D, int32_t M, 
     cudaStream_t stream = (cudaStream_t)stream_;
     g_launches = 0;
     GAPRO_REQUIRE(feats_spp && train_idx && test_idx && init_noise && ws && layout, "gapro_gp_debug_run: null pointer");
-    GAPRO_REQUIRE(M >= 1 && N >= 1 && layout_cap >= 31, "gapro_gp_debug_run: bad sizes");
+    GAPRO_REQUIRE(M >= 1 && N >= 1 && layout_cap >= 32, "gapro_gp_debug_run: bad sizes");
     std::vector<Region> all(1, make_region(M, N, n_b1, 0, 0, 0));
     const Layout l = make_layout(all[0].Mp, all[0].Np, all[0].Wp, D);
-    const long long vals[31] = {l.X,  l.Z,   l.Zm,    l.Zv,    l.gZ, l.Xt,   l.y, l.m,  l.mm, l.mv, l.scal,
+    const long long vals[32] = {l.X,  l.Z,   l.Zm,    l.Zv,    l.gZ, l.Xt,   l.y, l.m,  l.mm, l.mv, l.scal,
                                 l.mu, l.var, l.gmu,   l.gv,    l.gsrow, l.glrow, l.L, l.Linv, l.T, l.Tm, l.Tv,
-                                l.GA, l.GC,  l.Kzx,   l.A,     l.Bm, l.total, all[0].Mp, all[0].Np, all[0].Wp};
-    for (int i = 0; i < 31; ++i) layout[i] = vals[i];
+                                l.GA, l.GC,  l.Kzx,   l.A,     l.Bm, l.total, all[0].Mp, all[0].Np, all[0].Wp, l.Kc};
+    for (int i = 0; i < 32; ++i) layout[i] = vals[i];
     // status lives at the very end of the workspace for the debug run
     GAPRO_REQUIRE(ws_bytes >= 64, "gapro_gp_debug_run: workspace too small");
     int32_t* status = (int32_t*)((char*)ws + ws_bytes - 64);

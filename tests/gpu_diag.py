@@ -138,8 +138,6 @@ def section_phases():
     s = st(ph["GC"] + 1)
     print("  G_C:", rel(s["GC"][:M, :M], it["G_C"]))
     s = st(ph["GL"] + 1)
-    print("  G_L:", rel(s["GA"][:M, :M], it["G_L"]))
-    s = st(ph["SP"] + 1)
     print("  symP:", rel(s["Bm"][:M, :M], it["symP"]))
     s = st(ph["Y"] + 1)
     print("  Y:", rel(s["GA"][:M, :M], it["symP"] @ it["Linv"]))

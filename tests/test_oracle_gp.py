@@ -77,3 +77,22 @@ def test_finish_prediction_rule():
     assert out["label"].tolist() == [False, True, True]
     assert out["conf"][0] == np.float32(1.0) - out["prob"][0] and out["conf"][2] == out["prob"][2]
     assert out["prob"][1] == np.float32(0.5)
+
+
+def test_cholesky_adjoint_shortcut_used_by_the_cuda_path():
+    """The CUDA path never forms G_L: dLoss/dK_zz = -L^-T sym(Phi(G_A A^T)) L^-1, which must equal the
+    textbook L^-T sym(Phi(L^T G_L)) L^-1 with G_L = -tril(L^-T G_A A^T) of the oracle."""
+    rng = np.random.default_rng(3)
+    M, D = 23, 4
+    Z = rng.normal(size=(M, D))
+    X = Z + 0.1 * rng.normal(size=(M, D))
+    m = rng.normal(size=M) * 0.3
+    T = np.tril(rng.normal(size=(M, M)) * 0.2) + np.eye(M)
+    y = np.where(rng.random(M) < 0.5, -1.0, 1.0)
+    _, it = G.manual_grads(Z, m, T, 0.1, 0.2, -0.1, X, y, 1e-4, 1e-4, return_internals=True)
+    Q = it["G_A"] @ it["A"].T
+    phi = np.tril(Q)
+    phi[np.diag_indices(M)] *= 0.5
+    S = -0.5 * (phi + phi.T)
+    assert np.abs(S - it["symP"]).max() < 1e-14
+    assert np.abs(it["Linv"].T @ S @ it["Linv"] - it["G_K"]).max() < 1e-13
