@@ -159,22 +159,26 @@ __device__ __forceinline__ int swz(int k) { return ((k >> 2) & 1) | (((k >> 3) &
 template <bool KC>
 __device__ __forceinline__ int frag_row(int i, int g) { return KC ? 8 * i + g : 4 * g + i; }
 
+// Thread -> data map of the loaders: every warp-wide 16-byte cp.async lands on distinct banks
+// (k-contiguous tile: 4 rows x 8 units, bank = (row + unit) mod 8 with the 9-unit row stride;
+//  r-contiguous tile: one k-row x 32 units, XOR-swizzle permutes banks inside each group of 8).
 template <bool KC>
 __device__ __forceinline__ void load_stage(double* s, const double* g, int ld, int k) {
     const int t = threadIdx.x;
     if (KC) {
-        const int r = t >> 1, h = (t & 1) * 8;
-        const double* src = g + (size_t)r * ld + k + h;
-        double* dst = s + r * LDK + h;
+        const int u = t & 7, rr = t >> 3;                 // unit (2 doubles) in the row, row in the pass
+        const double* src = g + (size_t)rr * ld + k + 2 * u;
+        double* dst = s + rr * LDK + 2 * u;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cp_async16(dst + 2 * q, src + 2 * q);
+        for (int q = 0; q < 4; ++q) cp_async16(dst + q * 16 * LDK, src + (size_t)q * 16 * ld);
     } else {
-        const int kr = t >> 3, u = (t & 7) * 4;
+        const int u = t & 31, kr = t >> 5;                // unit in the k-row, k-row in the pass
         const double* src = g + (size_t)(k + kr) * ld + 2 * u;
-        double* dst = s + kr * TB;
-        const int x = swz(kr);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) cp_async16(dst + 2 * ((u + q) ^ x), src + 2 * q);
+        for (int q = 0; q < 4; ++q) {
+            const int kk = kr + 4 * q;
+            cp_async16(s + kk * TB + 2 * (u ^ swz(kk)), src + (size_t)4 * q * ld);
+        }
     }
 }
 
