@@ -617,9 +617,12 @@ k_rl_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, int
     }
 }
 
-// trailing update of block step kb over every lower tile (i, j) with i > kb
+// Trailing update with the block steps kb0 .. kb0+nk-1 (contraction over nk*64).  Updates are applied
+// two steps at a time: after an even step only the next block column / block row is brought up to date
+// (what the odd step's diag and panel need, nk = 1), after the odd step every remaining lower tile
+// receives both steps in one pass (nk = 2) - half the read-modify-write traffic of a per-step update.
 __global__ void __launch_bounds__(GEMM_THREADS, 4)
-k_rl_update(const Region* __restrict__ regs, const int4* __restrict__ tiles, int kb, GpParams prm,
+k_rl_update(const Region* __restrict__ regs, const int4* __restrict__ tiles, int kb0, int nk, GpParams prm,
             double* __restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_upd[];
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_upd);
@@ -630,28 +633,28 @@ k_rl_update(const Region* __restrict__ regs, const int4* __restrict__ tiles, int
     const int Mp = R.Mp;
     double* Lg = base + lay.L;
     double* Li = base + lay.Linv;
-    const int r0 = kb * TB, i0 = t.y * TB, j0 = t.z * TB;
+    const int k0 = kb0 * TB, k1 = (kb0 + nk) * TB, i0 = t.y * TB, j0 = t.z * TB;
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    if (t.z > kb) {
-        // K[i,j] -= L[i,kb] L[j,kb]^T   (pull the read-modify-write tile towards L2 while the product runs)
+    if (t.z >= kb0 + nk) {
+        // K[i,j] -= sum_k L[i,k] L[j,k]^T   (pull the read-modify-write tile towards L2 while the product runs)
         ACC_FOREACH(true, true, 0, 0, {
             (void)v0;
             (void)v1;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Lg + (size_t)(i0 + row) * Mp + j0 + col));
         })
-        gemm_accum<true, true>(acc, Lg + (size_t)i0 * Mp + r0, Mp, Lg + (size_t)j0 * Mp + r0, Mp, 0, TB, nullptr, sm);
+        gemm_accum<true, true>(acc, Lg + (size_t)i0 * Mp, Mp, Lg + (size_t)j0 * Mp, Mp, k0, k1, nullptr, sm);
         ACC_FOREACH(true, true, 0, 0, {
             double2* p = reinterpret_cast<double2*>(Lg + (size_t)(i0 + row) * Mp + j0 + col);
             const double2 k = __ldcg(p);
             *p = make_double2(k.x - v0, k.y - v1);
         })
     } else {
-        // S[i,j] (+)= L[i,kb] Linv[kb,j]
-        const bool first = t.z == kb;
+        // S[i,j] (+)= sum_k L[i,k] Linv[k,j]; the first contribution of a block column overwrites
+        const bool first = t.z >= kb0;
         if (!first) {
             ACC_FOREACH(true, false, 0, 0, {
                 (void)v0;
@@ -659,7 +662,7 @@ k_rl_update(const Region* __restrict__ regs, const int4* __restrict__ tiles, int
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(Li + (size_t)(i0 + row) * Mp + j0 + col));
             })
         }
-        gemm_accum<true, false>(acc, Lg + (size_t)i0 * Mp + r0, Mp, Li + (size_t)r0 * Mp + j0, Mp, 0, TB, nullptr, sm);
+        gemm_accum<true, false>(acc, Lg + (size_t)i0 * Mp, Mp, Li + j0, Mp, k0, k1, nullptr, sm);
         ACC_FOREACH(true, false, 0, 0, {
             double2* p = reinterpret_cast<double2*>(Li + (size_t)(i0 + row) * Mp + j0 + col);
             double2 o = make_double2(v0, v1);
@@ -790,11 +793,17 @@ k_grad_m(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPar
 }
 
 // Gradients w.r.t. the inducing points and the raw kernel parameters from G_K (in the B buffer,
-// symmetric) and G_C.  One warp per inducing row.
-template <int DMAX>
-__global__ void __launch_bounds__(256)
+// symmetric) and G_C.  A CTA owns 8*ROWS inducing rows (ROWS per warp); the Z / X rows of the
+// current block of 32 columns are staged once per CTA in shared memory (transposed, conflict-free),
+// lanes run over the 32 columns and the four matrix rows are read coalesced.
+template <int DMAX, int ROWS>
+__global__ void __launch_bounds__(256, (DMAX <= 8) ? 2 : 1)
 k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpParams prm, double* __restrict__ ws) {
-    const int2 rt = rtiles[blockIdx.x];
+    constexpr int SPLIT = TB / (8 * ROWS);           // CTAs per 64-row tile
+    __shared__ double Zs[DMAX][33];
+    __shared__ double Xs[DMAX][33];
+    __shared__ double Zi[8 * ROWS][DMAX];
+    const int2 rt = rtiles[blockIdx.x / SPLIT];
     const Region R = regs[rt.x];
     const int D = prm.D;
     const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
@@ -802,71 +811,82 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* sc = base + lay.scal;
     const double ell = softplus_d(sc[SC_RL]), s = softplus_d(sc[SC_RS]);
-    const double inv_l2 = 1.0 / (ell * ell);
+    const double inv_l2 = 1.0 / (ell * ell), inv_s = 1.0 / s, m2_ell = -2.0 / ell;
     const double* Z = base + lay.Z;
     const double* X = base + lay.X;
-    for (int rr = 0; rr < 8; ++rr) {
-        const int i = rt.y * TB + warp * 8 + rr;
-        if (i >= R.M) break;
-        double zi[DMAX], az[DMAX];
+    const int row0 = rt.y * TB + (blockIdx.x % SPLIT) * 8 * ROWS;
+    if (row0 >= R.M) return;
+    for (int e = threadIdx.x; e < 8 * ROWS * DMAX; e += blockDim.x) {
+        const int rr = e / DMAX, d = e - rr * DMAX;
+        Zi[rr][d] = (d < D && row0 + rr < R.M) ? Z[(size_t)(row0 + rr) * D + d] : 0.0;
+    }
+    double az[ROWS][DMAX], as[ROWS], al[ROWS], cz[ROWS];
 #pragma unroll
-        for (int d = 0; d < DMAX; ++d) {
-            zi[d] = d < D ? Z[(size_t)i * D + d] : 0.0;
-            az[d] = 0.0;
+    for (int q = 0; q < ROWS; ++q) {
+        as[q] = al[q] = cz[q] = 0.0;
+#pragma unroll
+        for (int d = 0; d < DMAX; ++d) az[q][d] = 0.0;
+    }
+    for (int jb = 0; jb < R.M; jb += 32) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * D; e += blockDim.x) {     // coalesced: rows jb..jb+31 are contiguous
+            const int jj = e / D, d = e - jj * D;
+            const bool ok = jb + jj < R.M;
+            Zs[d][jj] = ok ? Z[(size_t)jb * D + e] : 0.0;
+            Xs[d][jj] = ok ? X[(size_t)jb * D + e] : 0.0;
         }
-        double as = 0.0, al = 0.0;
-        const double* GK = base + lay.Bm + (size_t)i * R.Wp;
-        const double* GC = base + lay.GC + (size_t)i * R.Mp;
-        const double* Kx = base + lay.Kzx + (size_t)i * R.Wp;
-        const double* Kcr = base + lay.Kc + (size_t)i * R.Mp;
-        for (int j = lane; j < R.M; j += 32) {
-            // zz part: W = Gr + Gr^T = 2 Gr (G_K and K_zz symmetric); K_zz comes from the build phase
-            const double* zj = Z + (size_t)j * D;
-            double d2 = 0.0;
+        __syncthreads();
+        const int j = jb + lane;
+        if (j < R.M) {
+            double zj[DMAX], xj[DMAX];
 #pragma unroll
             for (int d = 0; d < DMAX; ++d) {
-                const double df = d < D ? zi[d] - zj[d] : 0.0;
-                d2 += df * df;
+                zj[d] = d < D ? Zs[d][lane] : 0.0;
+                xj[d] = d < D ? Xs[d][lane] : 0.0;
             }
-            double r2 = d2 * inv_l2;
-            const double Kz = Kcr[j];
-            double G = GK[j];
-            double Gr = -0.5 * G * Kz;
-            as += G * (Kz / s);
-            al += Gr * (-2.0 * r2 / ell);
 #pragma unroll
-            for (int d = 0; d < DMAX; ++d)
-                if (d < D) az[d] += 2.0 * Gr * (zi[d] - zj[d]);
-            // zx part
-            const double* xj = X + (size_t)j * D;
-            d2 = 0.0;
+            for (int q = 0; q < ROWS; ++q) {
+                const int rr = warp * ROWS + q, i = row0 + rr;
+                if (i < R.M) {
+                    const double gk = base[lay.Bm + (size_t)i * R.Wp + j], kz = base[lay.Kc + (size_t)i * R.Mp + j];
+                    const double gc = base[lay.GC + (size_t)i * R.Mp + j], kx = base[lay.Kzx + (size_t)i * R.Wp + j];
+                    double d2z = 0.0, d2x = 0.0;
 #pragma unroll
-            for (int d = 0; d < DMAX; ++d) {
-                const double df = d < D ? zi[d] - xj[d] : 0.0;
-                d2 += df * df;
+                    for (int d = 0; d < DMAX; ++d) {
+                        const double zi = Zi[rr][d];
+                        const double dz = zi - zj[d], dx = zi - xj[d];
+                        d2z = fma(dz, dz, d2z);
+                        d2x = fma(dx, dx, d2x);
+                    }
+                    // zz: W = Gr + Gr^T = 2 Gr (G_K, K_zz symmetric);  zx: Gr once.
+                    // sum_j [2 grz (z_i - z_j) + grx (z_i - x_j)] = z_i * cz - sum_j (2 grz z_j + grx x_j)
+                    const double grz2 = -gk * kz, grx = -0.5 * gc * kx;
+                    as[q] += (gk * kz + gc * kx) * inv_s;
+                    al[q] += (0.5 * grz2 * d2z + grx * d2x) * (inv_l2 * m2_ell);
+                    cz[q] += grz2 + grx;
+#pragma unroll
+                    for (int d = 0; d < DMAX; ++d) az[q][d] = fma(-grz2, zj[d], fma(-grx, xj[d], az[q][d]));
+                }
             }
-            r2 = d2 * inv_l2;
-            const double Kv = Kx[j];
-            G = GC[j];
-            Gr = -0.5 * G * Kv;
-            as += G * (Kv / s);
-            al += Gr * (-2.0 * r2 / ell);
-#pragma unroll
-            for (int d = 0; d < DMAX; ++d)
-                if (d < D) az[d] += Gr * (zi[d] - xj[d]);
         }
+    }
+#pragma unroll
+    for (int q = 0; q < ROWS; ++q) {
+        const int i = row0 + warp * ROWS + q;
+        double a0 = as[q], a1 = al[q], a2 = cz[q];
         for (int o = 16; o; o >>= 1) {
-            as += __shfl_xor_sync(0xffffffffu, as, o);
-            al += __shfl_xor_sync(0xffffffffu, al, o);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
 #pragma unroll
-            for (int d = 0; d < DMAX; ++d) az[d] += __shfl_xor_sync(0xffffffffu, az[d], o);
+            for (int d = 0; d < DMAX; ++d) az[q][d] += __shfl_xor_sync(0xffffffffu, az[q][d], o);
         }
-        if (lane == 0) {
-            base[lay.gsrow + i] = as;
-            base[lay.glrow + i] = al;
+        if (lane == 0 && i < R.M) {
+            base[lay.gsrow + i] = a0;
+            base[lay.glrow + i] = a1;
 #pragma unroll
             for (int d = 0; d < DMAX; ++d)
-                if (d < D) base[lay.gZ + (size_t)i * D + d] = 2.0 * inv_l2 * az[d];
+                if (d < D) base[lay.gZ + (size_t)i * D + d] = 2.0 * inv_l2 * fma(a2, Zi[warp * ROWS + q][d], az[q][d]);
         }
     }
 }
@@ -1075,6 +1095,7 @@ struct Driver {
     // chain of one group is scheduled ahead of the other groups' tile products instead of behind them
     cudaStream_t s_hi = nullptr, s_lo = nullptr;
     cudaEvent_t ev_swept = nullptr, ev_stepped = nullptr;
+    cudaEvent_t ev_prev_swept = nullptr;   // first sweep of the previous group: staggers the groups by one sweep
 
     void to_hi() {
         if (!s_hi) return;
@@ -1134,7 +1155,8 @@ struct Driver {
             }
             const int nu = tb.upd_off[kb + 1] - tb.upd_off[kb];
             if (nu > 0) {
-                k_rl_update<<<nu, GEMM_THREADS, GEMM_SMEM, stream>>>(tb.regs, tb.upd + tb.upd_off[kb], kb, p, ws);
+                const int kb0 = (kb & 1) ? kb - 1 : kb, nk = (kb & 1) ? 2 : 1;
+                k_rl_update<<<nu, GEMM_THREADS, GEMM_SMEM, stream>>>(tb.regs, tb.upd + tb.upd_off[kb], kb0, nk, p, ws);
                 ++g_launches;
             }
         }
@@ -1142,11 +1164,11 @@ struct Driver {
 
     void kgrad(const GpParams& p) {
         if (D <= 8)
-            k_kgrad<8><<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad<8, 4><<<tb.n_rows * 2, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         else if (D <= 32)
-            k_kgrad<32><<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad<32, 1><<<tb.n_rows * 8, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         else
-            k_kgrad<64><<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad<64, 1><<<tb.n_rows * 8, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         ++g_launches;
     }
 
@@ -1161,6 +1183,7 @@ struct Driver {
     prof_end(stream);                \
     ++ph;
         to_hi();
+        if (step == 1 && s_hi && ev_prev_swept) cudaStreamWaitEvent(s_hi, ev_prev_swept, 0);
         PHASE(build(p))
         PHASE(cholesky(p))
         to_lo();
@@ -1237,15 +1260,23 @@ int setup_chunk(std::vector<Region>& rs, char* aux, cudaStream_t stream, ChunkTa
     tb.rows = (int2*)put(rows.data(), rows.size() * 8);
     tb.rowsp = (int2*)put(rowsp.data(), rowsp.size() * 8);
     tb.panel = (int2*)put(panel.data(), panel.size() * 8);
-    // update tiles, step-major: step kb touches every lower tile (i, j <= i) with i > kb
+    // update tiles, step-major.  Even step kb: only block column kb+1 (K tiles) and block row kb+1
+    // (S tiles); odd step kb: every lower tile (i, j <= i) with i > kb, for both steps of the pair.
     std::vector<int4> upd;
     tb.upd_off.assign(tb.nbmax + 1, 0);
     for (int kb = 0; kb < tb.nbmax; ++kb) {
         tb.upd_off[kb] = (int)upd.size();
         const int live = tb.cnt_gt[kb];
-        for (int r = 0; r < live; ++r)
-            for (int i = rs[r].nb - 1; i > kb; --i)
-                for (int j = 0; j <= i; ++j) upd.push_back(make_int4(r, i, j, 0));
+        for (int r = 0; r < live; ++r) {
+            const int nb = rs[r].nb;
+            if (kb & 1) {
+                for (int i = nb - 1; i > kb; --i)
+                    for (int j = 0; j <= i; ++j) upd.push_back(make_int4(r, i, j, 0));
+            } else if (kb + 1 < nb) {
+                for (int i = nb - 1; i > kb; --i) upd.push_back(make_int4(r, i, kb + 1, 0));
+                for (int j = 0; j <= kb; ++j) upd.push_back(make_int4(r, kb + 1, j, 0));
+            }
+        }
     }
     tb.upd_off[tb.nbmax] = (int)upd.size();
     tb.upd = (int4*)put(upd.data(), upd.size() * 16);
@@ -1418,6 +1449,7 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
                 d.ev_swept = g_pool.swept[g];
                 d.ev_stepped = g_pool.stepped[g];
                 d.stream = d.s_hi;
+                if (g > 0 && !getenv("GAPRO_GP_NO_STAGGER")) d.ev_prev_swept = g_pool.swept[g - 1];
             }
             d.D = D;
             d.lr = lr;
