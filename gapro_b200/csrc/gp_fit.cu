@@ -489,17 +489,19 @@ k_build(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParam
 // Linv buffer until step i turns it into Linv[i,j].
 // ---------------------------------------------------------------------------------------------
 constexpr int LDS_ = TB + 1;
-constexpr int DIAG_SMEM = (2 * TB * LDS_ + 2 * TB) * (int)sizeof(double);
+constexpr int DIAG_SMEM = (2 * TB * LDS_ + TB) * (int)sizeof(double);
 
-// 64x64 factorisation + triangular inverse in shared memory.  Small loop bodies (no instruction
-// cache pressure), explicit 4-way batching so the shared-memory latency overlaps.
+// 64x64 factorisation + triangular inverse in shared memory, blocked by 16: the 16x16 diagonal blocks
+// are factored / inverted by one warp entirely in registers (rows or columns per lane, pivots and
+// multipliers exchanged with shuffles, no block barrier inside), the panel below is a per-row
+// forward substitution, trailing and off-diagonal blocks are small register-tiled products.
+// 12 block barriers for the factorisation and 4 for the inverse instead of ~320.
 __global__ void __launch_bounds__(GEMM_THREADS)
 k_rl_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __restrict__ ws, int32_t* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_diag[];
     double* sL = reinterpret_cast<double*>(smem_diag);   // [64][65] tile, then L
-    double* sX = sL + TB * LDS_;                         // [64][65] right-hand sides, then L^-1
-    double* lc = sX + TB * LDS_;                         // [64] current column of L
-    double* dinv = lc + TB;                              // [64] 1 / L[k][k]
+    double* sX = sL + TB * LDS_;                         // [64][65] L^-1
+    double* dinv = sX + TB * LDS_;                       // [64] 1 / L[k][k]
     const Region R = regs[blockIdx.x];
     const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
     double* base = ws + R.base;
@@ -507,72 +509,134 @@ k_rl_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __restr
     double* Lg = base + lay.L;
     double* Li = base + lay.Linv;
     const int r0 = kb * TB;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int e = tid; e < TB * TB; e += GEMM_THREADS) {
         const int r = e >> 6, c = e & 63;
         sL[r * LDS_ + c] = __ldcg(Lg + (size_t)(r0 + r) * Mp + r0 + c);
-        sX[r * LDS_ + c] = (r == c) ? 1.0 : 0.0;
+        sX[r * LDS_ + c] = 0.0;
     }
     __syncthreads();
-    const int r = tid & 63, half = tid >> 6;
     bool bad = false;
-    for (int c = 0; c < TB; ++c) {
-        double piv = sL[c * LDS_ + c];
-        if (!(piv > 0.0)) {
-            bad = true;
-            piv = 1.0;
-        }
-        const double rs = rsqrt(piv);
-        double l = 0.0;
-        if (half == 0 && r >= c) l = sL[r * LDS_ + c] * rs;      // r == c: piv * rsqrt(piv) = sqrt(piv)
-        __syncthreads();                                         // everyone has read the pivot
-        if (half == 0 && r >= c) {
-            sL[r * LDS_ + c] = l;
-            lc[r] = l;
-            if (r == c) dinv[c] = rs;
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
+        const int c0 = 16 * p;
+        // (a) 16x16 diagonal block: warp 0, lane r (and its mirror r+16) owns row r
+        if (warp == 0) {
+            const int r = lane & 15;
+            double a[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = sL[(c0 + r) * LDS_ + c0 + k];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                double piv = __shfl_sync(0xffffffffu, a[c], c);
+                if (!(piv > 0.0)) {
+                    bad = true;
+                    piv = 1.0;
+                }
+                const double rs = rsqrt(piv);
+                const double l = a[c] * rs;                 // lane c: piv * rsqrt(piv) = sqrt(piv)
+#pragma unroll
+                for (int cc = c + 1; cc < 16; ++cc) a[cc] = fma(-l, __shfl_sync(0xffffffffu, l, cc), a[cc]);
+                a[c] = l;
+                if (lane == c) dinv[c0 + c] = rs;
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) sL[(c0 + r) * LDS_ + c0 + k] = (k <= r) ? a[k] : 0.0;
+            }
         }
         __syncthreads();
-        if (r > c) {
-            const double lr = lc[r];
-            double* row = sL + r * LDS_;
-            int cc = c + 1 + half;
-            for (; cc + 6 <= r; cc += 8) {
-                const double v0 = row[cc], v1 = row[cc + 2], v2 = row[cc + 4], v3 = row[cc + 6];
-                const double w0 = lc[cc], w1 = lc[cc + 2], w2 = lc[cc + 4], w3 = lc[cc + 6];
-                row[cc] = fma(-lr, w0, v0);
-                row[cc + 2] = fma(-lr, w1, v1);
-                row[cc + 4] = fma(-lr, w2, v2);
-                row[cc + 6] = fma(-lr, w3, v3);
+        // (b) rows below the block: one thread per row, forward substitution against the 16x16 factor
+        const int nt = 48 - 16 * p;
+        if (tid < nt) {
+            const int r = c0 + 16 + tid;
+            double x[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = sL[r * LDS_ + c0 + k];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                double sum = x[c];
+#pragma unroll
+                for (int k = 0; k < c; ++k) sum = fma(-x[k], sL[(c0 + c) * LDS_ + c0 + k], sum);
+                x[c] = sum * dinv[c0 + c];
             }
-            for (; cc <= r; cc += 2) row[cc] = fma(-lr, lc[cc], row[cc]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sL[r * LDS_ + c0 + k] = x[k];
+        }
+        __syncthreads();
+        // (c) trailing update of the lower triangle: thread = (row, strip of columns)
+        if (nt > 0) {
+            const int nstrip = GEMM_THREADS / nt;
+            const int rr = tid % nt, strip = tid / nt;
+            if (strip < nstrip) {
+                const int r = c0 + 16 + rr;
+                double lr[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) lr[k] = sL[r * LDS_ + c0 + k];
+                for (int cc = c0 + 16 + strip; cc <= r; cc += nstrip) {
+                    double sum = sL[r * LDS_ + cc];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) sum = fma(-lr[k], sL[cc * LDS_ + c0 + k], sum);
+                    sL[r * LDS_ + cc] = sum;
+                }
+            }
         }
         __syncthreads();
     }
     if (bad && tid == 0) atomicOr(status + R.orig, GAPRO_GP_NOT_PSD);
-    // inverse by column-oriented forward substitution: thread (c, half) owns the rows of column c with
-    // parity `half`; b lives in sX[:, c]
+    // ---- inverse.  Diagonal 16x16 blocks: warp p, lane c (and mirror) owns column c.
     {
-        const int c = r;
-        for (int k = 0; k < TB; ++k) {
-            const double xk = sX[k * LDS_ + c] * dinv[k];
-            __syncthreads();                     // both owners have read b[k]
-            if (half == 0) sX[k * LDS_ + c] = xk;
-            if (k >= c) {
-                int q = k + 1 + ((k + 1 + half) & 1);        // first row > k with parity `half`
-                for (; q + 6 < TB; q += 8) {
-                    const double b0 = sX[q * LDS_ + c], b1 = sX[(q + 2) * LDS_ + c], b2 = sX[(q + 4) * LDS_ + c],
-                                 b3 = sX[(q + 6) * LDS_ + c];
-                    const double l0 = sL[q * LDS_ + k], l1 = sL[(q + 2) * LDS_ + k], l2 = sL[(q + 4) * LDS_ + k],
-                                 l3 = sL[(q + 6) * LDS_ + k];
-                    sX[q * LDS_ + c] = fma(-l0, xk, b0);
-                    sX[(q + 2) * LDS_ + c] = fma(-l1, xk, b1);
-                    sX[(q + 4) * LDS_ + c] = fma(-l2, xk, b2);
-                    sX[(q + 6) * LDS_ + c] = fma(-l3, xk, b3);
-                }
-                for (; q < TB; q += 2) sX[q * LDS_ + c] = fma(-sL[q * LDS_ + k], xk, sX[q * LDS_ + c]);
-            }
-            __syncthreads();
+        const int c0 = 16 * warp, c = lane & 15;
+        double x[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            double sum = (q == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < q; ++k) sum = fma(-sL[(c0 + q) * LDS_ + c0 + k], x[k], sum);
+            x[q] = sum * dinv[c0 + q];
         }
+        if (lane < 16) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) sX[(c0 + q) * LDS_ + c0 + c] = (q >= c) ? x[q] : 0.0;
+        }
+    }
+    __syncthreads();
+    // Off-diagonal blocks by distance d = i - j:  X_ij = -X_ii * sum_{k=j..i-1} L_ik X_kj.
+    // One warp per block; lane = (row r, half h of the 16 columns).
+#pragma unroll 1
+    for (int d = 1; d < 4; ++d) {
+        if (warp < 4 - d) {
+            const int i = warp + d, j = warp;
+            const int r = lane & 15, h = lane >> 4;
+            double t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t[q] = 0.0;
+            const double* Lrow = sL + (16 * i + r) * LDS_ + 16 * j;            // L[i-block row r][cols of blocks j..i-1]
+            for (int kk = 0; kk < 16 * d; ++kk) {
+                const double lv = Lrow[kk];
+                const double* xr = sX + (16 * j + kk) * LDS_ + 16 * j + 8 * h;  // X[(blocks j..i-1) row kk][block j cols]
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t[q] = fma(lv, xr[q], t[q]);
+            }
+            // stage T in the destination block, then out = -X_ii * T
+            double* Tb = sX + (16 * i) * LDS_ + 16 * j;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) Tb[r * LDS_ + 8 * h + q] = t[q];
+            __syncwarp();
+            double o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = 0.0;
+            const double* Xii = sX + (16 * i + r) * LDS_ + 16 * i;
+            for (int m = 0; m <= r; ++m) {
+                const double xv = Xii[m];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = fma(-xv, Tb[m * LDS_ + 8 * h + q], o[q]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) Tb[r * LDS_ + 8 * h + q] = o[q];
+        }
+        __syncthreads();
     }
     for (int e = tid; e < TB * TB; e += GEMM_THREADS) {
         const int rr = e >> 6, c = e & 63;
