@@ -1463,6 +1463,17 @@ static int set_kernel_attributes() {
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GL>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_Y>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GK>, GEMM_SMEM);
+    if (!getenv("GAPRO_GP_DEFAULT_CARVEOUT")) {
+        // the element-wise kernels too: a kernel that prefers a large L1 cannot share an SM with the tile
+        // kernels of another group, which would serialise the side streams
+        if (rc == GAPRO_OK) rc = allow_smem(k_colstats, 0);
+        if (rc == GAPRO_OK) rc = allow_smem(k_grad_m, 0);
+        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<8, 4>, 0);
+        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<32, 1>, 0);
+        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<64, 1>, 0);
+        if (rc == GAPRO_OK) rc = allow_smem(k_adam_small, 0);
+        if (rc == GAPRO_OK) rc = allow_smem(k_region_init, 0);
+    }
     done = rc == GAPRO_OK;
     return rc;
 }

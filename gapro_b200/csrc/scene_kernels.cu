@@ -330,7 +330,7 @@ __device__ __forceinline__ int warp_find_scene(const int32_t* __restrict__ spp_o
 }
 
 template <int WORDS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 k_occupancy(const double* __restrict__ xyz, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
             const int32_t* __restrict__ spp_off, const int32_t* __restrict__ box_off, const double* __restrict__ boxes,
             int n_scenes, int s_total, double margin, float thresh, uint32_t* __restrict__ occ_bits,
@@ -475,50 +475,80 @@ extern "C" int gapro_occupancy(const double* xyz, const int32_t* perm, const int
 // =============================================================================================
 // B — feature pooling (gen_ps_utils.py:357): float32 sum in point-index order, / float32 count
 // =============================================================================================
-// One warp per superpoint.  For every chunk of 32 points the warp loads the point indices with one
-// coalesced read, issues all D*32 feature gathers at once (independent loads, one memory latency),
-// stages them in shared memory, and lanes d < D then replay the float32 adds strictly in point
-// order — the index-ordered float32 sum of torch_scatter's CPU kernel, bit for bit.
+// A warp owns POOL_U consecutive superpoints and walks them in lock-step so that the dependent
+// loads of the chain seg_off -> perm -> features are issued for all of them before any is consumed
+// (POOL_U independent memory latencies in flight per warp).  Per superpoint and chunk of 32 points:
+// one coalesced read of the point indices, D*32 independent feature gathers staged in shared
+// memory, then lanes d < D replay the float32 adds strictly in point order — the index-ordered
+// float32 sum of torch_scatter's CPU kernel, bit for bit.
 constexpr int POOL_WARPS = 8;
 
+template <int U>
 __global__ void __launch_bounds__(32 * POOL_WARPS)
 k_pool_feats(const float* __restrict__ feats, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
              int s_total, int D, float* __restrict__ out) {
-    extern __shared__ float pool_smem[];               // [POOL_WARPS][32 * D]
+    extern __shared__ float pool_smem[];               // [POOL_WARPS][U][32 * D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = blockIdx.x * POOL_WARPS + warp;
-    if (g >= s_total) return;
-    float* stage = pool_smem + (size_t)warp * 32 * D;
-    const int start = seg_off[g], end = seg_off[g + 1];
-    float acc[2] = {0.0f, 0.0f};                       // lane handles dims lane and lane + 32 (D <= 64)
-    for (int base = start; base < end; base += 32) {
-        const int n = min(32, end - base);
-        const int myp = (lane < n) ? perm[base + lane] : 0;
-        const int total = n * D;
-        for (int e0 = 0; e0 < total; e0 += 32) {           // warp-uniform trip count (full-mask shuffles)
-            const int e = e0 + lane;
-            const int ec = min(e, total - 1);
-            const int pt = ec / D, d = ec - pt * D;
-            const int p = __shfl_sync(FULL_MASK, myp, pt);
-            if (e < total) stage[e] = feats[(int64_t)p * D + d];
+    const int g0 = (blockIdx.x * POOL_WARPS + warp) * U;
+    if (g0 >= s_total) return;
+    float* stage = pool_smem + (size_t)warp * U * 32 * D;
+    int start[U], end[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int g = min(g0 + u, s_total - 1);
+        start[u] = seg_off[g];
+        end[u] = (g0 + u < s_total) ? seg_off[g + 1] : start[u];     // empty when past the last superpoint
+    }
+    float acc[U][2];                                   // lane handles dims lane and lane + 32 (D <= 64)
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u][0] = acc[u][1] = 0.0f;
+    int longest = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) longest = max(longest, end[u] - start[u]);
+    for (int off = 0; off < longest; off += 32) {
+        int n[U], myp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            n[u] = max(0, min(32, end[u] - start[u] - off));
+            myp[u] = (lane < n[u]) ? perm[start[u] + off + lane] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int total = n[u] * D;
+            float* st = stage + u * 32 * D;
+            for (int e0 = 0; e0 < total; e0 += 32) {       // warp-uniform trip count (full-mask shuffles)
+                const int e = e0 + lane;
+                const int ec = min(e, total - 1);
+                const int pt = ec / D, d = ec - pt * D;
+                const int p = __shfl_sync(FULL_MASK, myp[u], pt);
+                if (e < total) st[e] = feats[(int64_t)p * D + d];
+            }
         }
         __syncwarp();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int d = lane + 32 * h;
-            if (d < D) {
-                float a = acc[h];
-                for (int pt = 0; pt < n; ++pt) a = __fadd_rn(a, stage[pt * D + d]);
-                acc[h] = a;
+        for (int u = 0; u < U; ++u) {
+            const float* st = stage + u * 32 * D;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int d = lane + 32 * h;
+                if (d < D) {
+                    float a = acc[u][h];
+                    for (int pt = 0; pt < n[u]; ++pt) a = __fadd_rn(a, st[pt * D + d]);
+                    acc[u][h] = a;
+                }
             }
         }
         __syncwarp();
     }
-    const float fcnt = (float)(end - start);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int d = lane + 32 * h;
-        if (d < D) out[(int64_t)g * D + d] = __fdiv_rn(acc[h], fcnt);
+    for (int u = 0; u < U; ++u) {
+        if (g0 + u >= s_total) break;
+        const float fcnt = (float)(end[u] - start[u]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int d = lane + 32 * h;
+            if (d < D) out[(int64_t)(g0 + u) * D + d] = __fdiv_rn(acc[u][h], fcnt);
+        }
     }
 }
 
@@ -528,16 +558,21 @@ extern "C" int gapro_pool_feats(const float* feats, const int32_t* perm, const i
     GAPRO_REQUIRE(feats && perm && seg_off && out, "gapro_pool_feats: null pointer");
     GAPRO_REQUIRE(s_total > 0 && D > 0, "gapro_pool_feats: empty input");
     GAPRO_REQUIRE(D <= 64, "gapro_pool_feats: feature dimension %d > 64", D);
-    const size_t smem = (size_t)POOL_WARPS * 32 * D * sizeof(float);
-    if (smem > 48 * 1024) {
-        static bool attr = false;
-        if (!attr) {
-            GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_pool_feats, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            attr = true;
-        }
+    static bool attr = false;
+    if (!attr) {
+        GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_pool_feats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
     }
-    k_pool_feats<<<(unsigned)((s_total + POOL_WARPS - 1) / POOL_WARPS), 32 * POOL_WARPS, smem, stream>>>(
-        feats, perm, seg_off, s_total, D, out);
+    if (D <= 8) {          // 4 superpoints per warp in lock-step
+        const size_t smem = (size_t)POOL_WARPS * 4 * 32 * D * sizeof(float);
+        const int per_cta = POOL_WARPS * 4;
+        k_pool_feats<4><<<(unsigned)((s_total + per_cta - 1) / per_cta), 32 * POOL_WARPS, smem, stream>>>(
+            feats, perm, seg_off, s_total, D, out);
+    } else {
+        const size_t smem = (size_t)POOL_WARPS * 32 * D * sizeof(float);
+        k_pool_feats<1><<<(unsigned)((s_total + POOL_WARPS - 1) / POOL_WARPS), 32 * POOL_WARPS, smem, stream>>>(
+            feats, perm, seg_off, s_total, D, out);
+    }
     GAPRO_KERNEL_CHECK();
     return GAPRO_OK;
 }
