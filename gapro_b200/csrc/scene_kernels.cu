@@ -308,13 +308,30 @@ extern "C" int gapro_floor_boxes(const double* xyz, const int64_t* pt_off_dev, c
 // and "disjoint" (count = 0) are decided without touching the points again — exact, because the
 // containment test is a conjunction of per-axis interval tests — and only boxes that cut through the
 // superpoint are counted point by point with a warp ballot.
+// Warp-wide min / max of doubles with two integer REDUX operations each: doubles are mapped to
+// order-preserving uint64 keys, the high words are reduced first, then the low words among the
+// lanes that hold the winning high word.  Exact (no floating-point arithmetic involved).
+__device__ __forceinline__ unsigned long long dbl_key(double d) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_dbl(unsigned long long u) {
+    unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)b);
+}
 __device__ __forceinline__ double warp_min(double v) {
-    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL_MASK, v, o));
-    return v;
+    const unsigned long long u = dbl_key(v);
+    const unsigned hi = (unsigned)(u >> 32), lo = (unsigned)u;
+    const unsigned mhi = __reduce_min_sync(FULL_MASK, hi);
+    const unsigned mlo = __reduce_min_sync(FULL_MASK, hi == mhi ? lo : 0xffffffffu);
+    return key_dbl(((unsigned long long)mhi << 32) | mlo);
 }
 __device__ __forceinline__ double warp_max(double v) {
-    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
-    return v;
+    const unsigned long long u = dbl_key(v);
+    const unsigned hi = (unsigned)(u >> 32), lo = (unsigned)u;
+    const unsigned mhi = __reduce_max_sync(FULL_MASK, hi);
+    const unsigned mlo = __reduce_max_sync(FULL_MASK, hi == mhi ? lo : 0u);
+    return key_dbl(((unsigned long long)mhi << 32) | mlo);
 }
 
 // scene of global superpoint g: one coalesced load of the offsets + a ballot instead of a chain of
@@ -330,7 +347,7 @@ __device__ __forceinline__ int warp_find_scene(const int32_t* __restrict__ spp_o
 }
 
 template <int WORDS>
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256)
 k_occupancy(const double* __restrict__ xyz, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
             const int32_t* __restrict__ spp_off, const int32_t* __restrict__ box_off, const double* __restrict__ boxes,
             int n_scenes, int s_total, double margin, float thresh, uint32_t* __restrict__ occ_bits,
@@ -473,82 +490,238 @@ extern "C" int gapro_occupancy(const double* xyz, const int32_t* perm, const int
 }
 
 // =============================================================================================
-// B — feature pooling (gen_ps_utils.py:357): float32 sum in point-index order, / float32 count
+// Heuristic labelers: gen_pseudo_label_box2mask (gen_ps_utils.py:242-290) and
+// gen_pseudo_label (:485-569) + spp_align_label (:99-129).  Per-POINT containment in the instance
+// boxes (margins evaluated in float32, the dtype of instance_box there), per-point rule for points
+// in several boxes (smallest volume / nearest centre / none), then a majority vote per superpoint
+// over the labels {background, box 0, box 1, ...} (first maximum wins), optionally restricted to
+// boxes that hold >= occ_thresh of the superpoint.  One warp per superpoint, same extent
+// pre-classification as k_occupancy.
 // =============================================================================================
-// A warp owns POOL_U consecutive superpoints and walks them in lock-step so that the dependent
-// loads of the chain seg_off -> perm -> features are issued for all of them before any is consumed
-// (POOL_U independent memory latencies in flight per warp).  Per superpoint and chunk of 32 points:
-// one coalesced read of the point indices, D*32 independent feature gathers staged in shared
-// memory, then lanes d < D replay the float32 adds strictly in point order — the index-ordered
-// float32 sum of torch_scatter's CPU kernel, bit for bit.
-constexpr int POOL_WARPS = 8;
-
-template <int U>
-__global__ void __launch_bounds__(32 * POOL_WARPS)
-k_pool_feats(const float* __restrict__ feats, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
-             int s_total, int D, float* __restrict__ out) {
-    extern __shared__ float pool_smem[];               // [POOL_WARPS][U][32 * D]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g0 = (blockIdx.x * POOL_WARPS + warp) * U;
-    if (g0 >= s_total) return;
-    float* stage = pool_smem + (size_t)warp * U * 32 * D;
-    int start[U], end[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int g = min(g0 + u, s_total - 1);
-        start[u] = seg_off[g];
-        end[u] = (g0 + u < s_total) ? seg_off[g + 1] : start[u];     // empty when past the last superpoint
+template <int WORDS>
+__global__ void __launch_bounds__(256)
+k_heuristic(const double* __restrict__ xyz, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
+            const int32_t* __restrict__ spp_off, const int32_t* __restrict__ box_off, const float* __restrict__ boxes,
+            const float* __restrict__ vol, int n_scenes, int s_total, int rule, int spp_align, float occ_thresh,
+            int32_t* __restrict__ inst_spp, int32_t* __restrict__ inst_pt) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= s_total) return;
+    const int start = seg_off[g], end = seg_off[g + 1];
+    const int cnt = end - start;
+    const int sc = warp_find_scene(spp_off, n_scenes, g, lane);
+    const int b0 = box_off[sc];
+    const int nb = box_off[sc + 1] - b0;
+    const float MARGIN = 0.005f;
+    // extent of the superpoint
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double lx = INF, ly = INF, lz = INF, hx = -INF, hy = -INF, hz = -INF;
+    for (int k = start + lane; k < end; k += 32) {
+        const int64_t p = perm[k];
+        const double x = xyz[3 * p], y = xyz[3 * p + 1], z = xyz[3 * p + 2];
+        lx = fmin(lx, x); ly = fmin(ly, y); lz = fmin(lz, z);
+        hx = fmax(hx, x); hy = fmax(hy, y); hz = fmax(hz, z);
     }
-    float acc[U][2];                                   // lane handles dims lane and lane + 32 (D <= 64)
+    lx = warp_min(lx); ly = warp_min(ly); lz = warp_min(lz);
+    hx = warp_max(hx); hy = warp_max(hy); hz = warp_max(hz);
+    // classify the boxes: lane b of word w looks at box 32w+b
+    uint32_t all_in[WORDS], cuts[WORDS];
 #pragma unroll
-    for (int u = 0; u < U; ++u) acc[u][0] = acc[u][1] = 0.0f;
-    int longest = 0;
-#pragma unroll
-    for (int u = 0; u < U; ++u) longest = max(longest, end[u] - start[u]);
-    for (int off = 0; off < longest; off += 32) {
-        int n[U], myp[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            n[u] = max(0, min(32, end[u] - start[u] - off));
-            myp[u] = (lane < n[u]) ? perm[start[u] + off + lane] : 0;
+    for (int w = 0; w < WORDS; ++w) {
+        const int b = 32 * w + lane;
+        bool contains = false, partial = false;
+        if (b < nb) {
+            const float* bx = boxes + 6 * (size_t)(b0 + b);
+            const double l0 = (double)__fsub_rn(bx[0], MARGIN), l1 = (double)__fsub_rn(bx[1], MARGIN),
+                         l2 = (double)__fsub_rn(bx[2], MARGIN);
+            const double h0 = (double)__fadd_rn(bx[3], MARGIN), h1 = (double)__fadd_rn(bx[4], MARGIN),
+                         h2 = (double)__fadd_rn(bx[5], MARGIN);
+            contains = lx >= l0 && ly >= l1 && lz >= l2 && hx <= h0 && hy <= h1 && hz <= h2;
+            const bool disjoint = hx < l0 || hy < l1 || hz < l2 || lx > h0 || ly > h1 || lz > h2;
+            partial = !contains && !disjoint;
         }
+        all_in[w] = __ballot_sync(FULL_MASK, contains);
+        cuts[w] = __ballot_sync(FULL_MASK, partial);
+    }
+    int votes[WORDS], inside[WORDS];      // lane b of word w: votes / points inside for box 32w+b
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int total = n[u] * D;
-            float* st = stage + u * 32 * D;
-            for (int e0 = 0; e0 < total; e0 += 32) {       // warp-uniform trip count (full-mask shuffles)
-                const int e = e0 + lane;
-                const int ec = min(e, total - 1);
-                const int pt = ec / D, d = ec - pt * D;
-                const int p = __shfl_sync(FULL_MASK, myp[u], pt);
-                if (e < total) st[e] = feats[(int64_t)p * D + d];
+    for (int w = 0; w < WORDS; ++w) votes[w] = inside[w] = 0;
+    int votes_bg = 0;
+    for (int base = start; base < end; base += 32) {
+        const int k = base + lane;
+        const bool valid = k < end;
+        int64_t p = 0;
+        double x = 0, y = 0, z = 0;
+        if (valid) {
+            p = perm[k];
+            x = xyz[3 * p];
+            y = xyz[3 * p + 1];
+            z = xyz[3 * p + 2];
+        }
+        // per-point containment mask
+        uint32_t mask[WORDS];
+        int n_in = 0;
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) {
+            uint32_t m = valid ? all_in[w] : 0u;
+            uint32_t c = cuts[w];
+            while (c) {
+                const int bb = __ffs(c) - 1;
+                c &= c - 1;
+                const float* bx = boxes + 6 * (size_t)(b0 + 32 * w + bb);
+                const bool in = valid && x >= (double)__fsub_rn(bx[0], MARGIN) && y >= (double)__fsub_rn(bx[1], MARGIN) &&
+                                z >= (double)__fsub_rn(bx[2], MARGIN) && x <= (double)__fadd_rn(bx[3], MARGIN) &&
+                                y <= (double)__fadd_rn(bx[4], MARGIN) && z <= (double)__fadd_rn(bx[5], MARGIN);
+                m |= (uint32_t)in << bb;
             }
+            mask[w] = m;
+            n_in += __popc(m);
         }
-        __syncwarp();
+        // label: 0 background, b+1 box b, (rule "none": several boxes -> background for the vote, -2 per point)
+        int label = 0;
+        if (n_in == 1) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float* st = stage + u * 32 * D;
+            for (int w = 0; w < WORDS; ++w)
+                if (mask[w]) label = 32 * w + __ffs(mask[w]);
+        } else if (n_in > 1 && rule != 2) {
+            double best = 0.0;
+            int arg = -1;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int d = lane + 32 * h;
-                if (d < D) {
-                    float a = acc[u][h];
-                    for (int pt = 0; pt < n[u]; ++pt) a = __fadd_rn(a, st[pt * D + d]);
-                    acc[u][h] = a;
+            for (int w = 0; w < WORDS; ++w) {
+                uint32_t m = mask[w];
+                while (m) {
+                    const int b = 32 * w + __ffs(m) - 1;
+                    m &= m - 1;
+                    double key;
+                    if (rule == 0) {
+                        key = (double)vol[b0 + b];
+                    } else {
+                        const float* bx = boxes + 6 * (size_t)(b0 + b);
+                        const double cx = (double)__fdiv_rn(__fadd_rn(bx[0], bx[3]), 2.0f);
+                        const double cy = (double)__fdiv_rn(__fadd_rn(bx[1], bx[4]), 2.0f);
+                        const double cz = (double)__fdiv_rn(__fadd_rn(bx[2], bx[5]), 2.0f);
+                        const double dx = __dsub_rn(x, cx), dy = __dsub_rn(y, cy), dz = __dsub_rn(z, cz);
+                        key = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    }
+                    if (arg < 0 || key < best) {
+                        best = key;
+                        arg = b;
+                    }
+                }
+            }
+            label = arg + 1;
+        }
+        if (!spp_align && valid) inst_pt[p] = (n_in > 1 && rule == 2) ? -2 : label - 1;
+        // votes of this chunk
+        votes_bg += __popc(__ballot_sync(FULL_MASK, valid && label == 0));
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) {
+            uint32_t cand = all_in[w] | cuts[w];
+            while (cand) {
+                const int bb = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const int v = __popc(__ballot_sync(FULL_MASK, valid && label == 32 * w + bb + 1));
+                const int c = __popc(__ballot_sync(FULL_MASK, (mask[w] >> bb) & 1u));
+                if (lane == bb) {
+                    votes[w] += v;
+                    inside[w] += c;
                 }
             }
         }
-        __syncwarp();
     }
+    if (!spp_align) return;
+    // majority vote (first maximum wins: background first, then boxes in increasing index)
+    uint32_t best_key = ((uint32_t)votes_bg << 10) | 1023u;            // key = votes * 1024 + (1023 - label)
+    const float fcnt = (float)cnt;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        if (g0 + u >= s_total) break;
-        const float fcnt = (float)(end[u] - start[u]);
+    for (int w = 0; w < WORDS; ++w) {
+        int v = votes[w];
+        if (occ_thresh >= 0.0f && !(__fdiv_rn((float)inside[w], fcnt) >= occ_thresh)) v = 0;
+        const int label = 32 * w + lane + 1;
+        const uint32_t key = (32 * w + lane < nb) ? (((uint32_t)v << 10) | (uint32_t)(1023 - label)) : 0u;
+        const uint32_t m = __reduce_max_sync(FULL_MASK, key);
+        best_key = m > best_key ? m : best_key;
+    }
+    if (lane == 0) inst_spp[g] = (int)(1023u - (best_key & 1023u)) - 1;      // label - 1: -1 = background
+}
+
+extern "C" int gapro_heuristic_labels(const double* xyz, const int32_t* perm, const int32_t* seg_off,
+                                      const int32_t* spp_off_dev, const int32_t* box_off_dev, const float* boxes,
+                                      const float* boxes_vol, int32_t n_scenes, int32_t s_total, int32_t words,
+                                      int32_t rule, int32_t spp_align, float occ_thresh, int32_t* inst_spp,
+                                      int32_t* inst_pt, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GAPRO_REQUIRE(xyz && perm && seg_off && spp_off_dev && box_off_dev && boxes && boxes_vol, "gapro_heuristic_labels: null pointer");
+    GAPRO_REQUIRE(spp_align ? inst_spp != nullptr : inst_pt != nullptr, "gapro_heuristic_labels: missing output array");
+    GAPRO_REQUIRE(rule >= 0 && rule <= 2, "gapro_heuristic_labels: rule must be 0 (volume), 1 (dist) or 2 (none)");
+    GAPRO_REQUIRE(n_scenes > 0 && s_total > 0, "gapro_heuristic_labels: empty batch");
+    GAPRO_REQUIRE(words == 1 || words == 2 || words == 4 || words == 8,
+                  "gapro_heuristic_labels: words must be 1, 2, 4 or 8 (at most 256 boxes per scene)");
+    const int T = 256, WPB = T / 32;
+    unsigned G = (unsigned)((s_total + WPB - 1) / WPB);
+#define LAUNCH_H(W)                                                                                                 \
+    k_heuristic<W><<<G, T, 0, stream>>>(xyz, perm, seg_off, spp_off_dev, box_off_dev, boxes, boxes_vol, n_scenes,   \
+                                        s_total, rule, spp_align, occ_thresh, inst_spp, inst_pt)
+    switch (words) {
+        case 1: LAUNCH_H(1); break;
+        case 2: LAUNCH_H(2); break;
+        case 4: LAUNCH_H(4); break;
+        default: LAUNCH_H(8); break;
+    }
+#undef LAUNCH_H
+    GAPRO_KERNEL_CHECK();
+    return GAPRO_OK;
+}
+
+// =============================================================================================
+// B — feature pooling (gen_ps_utils.py:357): float32 sum in point-index order, / float32 count
+// =============================================================================================
+// One warp per superpoint.  For every chunk of 32 points the warp loads the point indices with one
+// coalesced read, issues all D*32 feature gathers at once (independent loads, one memory latency),
+// stages them in shared memory, and lanes d < D then replay the float32 adds strictly in point
+// order — the index-ordered float32 sum of torch_scatter's CPU kernel, bit for bit.
+constexpr int POOL_WARPS = 8;
+
+template <int DT>     // DT > 0: feature dimension known at compile time (cheap index arithmetic); 0: runtime D
+__global__ void __launch_bounds__(32 * POOL_WARPS)
+k_pool_feats(const float* __restrict__ feats, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
+             int s_total, int D_, float* __restrict__ out) {
+    const int D = DT > 0 ? DT : D_;
+    extern __shared__ float pool_smem[];               // [POOL_WARPS][32 * D]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x * POOL_WARPS + warp;
+    if (g >= s_total) return;
+    float* stage = pool_smem + (size_t)warp * 32 * D;
+    const int start = seg_off[g], end = seg_off[g + 1];
+    float acc[2] = {0.0f, 0.0f};                       // lane handles dims lane and lane + 32 (D <= 64)
+    for (int base = start; base < end; base += 32) {
+        const int n = min(32, end - base);
+        const int myp = (lane < n) ? perm[base + lane] : 0;
+        const int total = n * D;
+        for (int e0 = 0; e0 < total; e0 += 32) {           // warp-uniform trip count (full-mask shuffles)
+            const int e = e0 + lane;
+            const int ec = min(e, total - 1);
+            const int pt = ec / D, d = ec - pt * D;
+            const int p = __shfl_sync(FULL_MASK, myp, pt);
+            if (e < total) stage[e] = feats[(int64_t)p * D + d];
+        }
+        __syncwarp();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int d = lane + 32 * h;
-            if (d < D) out[(int64_t)(g0 + u) * D + d] = __fdiv_rn(acc[u][h], fcnt);
+            if (d < D) {
+                float a = acc[h];
+                for (int pt = 0; pt < n; ++pt) a = __fadd_rn(a, stage[pt * D + d]);
+                acc[h] = a;
+            }
         }
+        __syncwarp();
+    }
+    const float fcnt = (float)(end - start);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int d = lane + 32 * h;
+        if (d < D) out[(int64_t)g * D + d] = __fdiv_rn(acc[h], fcnt);
     }
 }
 
@@ -558,21 +731,19 @@ extern "C" int gapro_pool_feats(const float* feats, const int32_t* perm, const i
     GAPRO_REQUIRE(feats && perm && seg_off && out, "gapro_pool_feats: null pointer");
     GAPRO_REQUIRE(s_total > 0 && D > 0, "gapro_pool_feats: empty input");
     GAPRO_REQUIRE(D <= 64, "gapro_pool_feats: feature dimension %d > 64", D);
+    const size_t smem = (size_t)POOL_WARPS * 32 * D * sizeof(float);
     static bool attr = false;
     if (!attr) {
-        GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_pool_feats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_pool_feats<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr = true;
     }
-    if (D <= 8) {          // 4 superpoints per warp in lock-step
-        const size_t smem = (size_t)POOL_WARPS * 4 * 32 * D * sizeof(float);
-        const int per_cta = POOL_WARPS * 4;
-        k_pool_feats<4><<<(unsigned)((s_total + per_cta - 1) / per_cta), 32 * POOL_WARPS, smem, stream>>>(
-            feats, perm, seg_off, s_total, D, out);
-    } else {
-        const size_t smem = (size_t)POOL_WARPS * 32 * D * sizeof(float);
-        k_pool_feats<1><<<(unsigned)((s_total + POOL_WARPS - 1) / POOL_WARPS), 32 * POOL_WARPS, smem, stream>>>(
-            feats, perm, seg_off, s_total, D, out);
-    }
+    const unsigned grid = (unsigned)((s_total + POOL_WARPS - 1) / POOL_WARPS);
+    if (D == 6)
+        k_pool_feats<6><<<grid, 32 * POOL_WARPS, smem, stream>>>(feats, perm, seg_off, s_total, D, out);
+    else if (D == 32)
+        k_pool_feats<32><<<grid, 32 * POOL_WARPS, smem, stream>>>(feats, perm, seg_off, s_total, D, out);
+    else
+        k_pool_feats<0><<<grid, 32 * POOL_WARPS, smem, stream>>>(feats, perm, seg_off, s_total, D, out);
     GAPRO_KERNEL_CHECK();
     return GAPRO_OK;
 }

@@ -318,6 +318,68 @@ class GaproEngine:
                                         **{k: v[q0:q1] for k, v in res.items()}))
         return out, dbg
 
+    # ------------------------------------------------------------------ heuristic labelers
+    def run_heuristic(self, coords_float, spp, instance_cls, instance_box, instance_box_volume, instance_classes=18,
+                      rule="volume", spp_align=True, occ_thresh=None):
+        """One scene through the heuristic labelers: per-point containment in the instance boxes, the rule
+        for points in several boxes, optional majority vote per superpoint.  Returns (sem[N] i32, inst[N] i32)."""
+        lib, dev = self.lib, self.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        xyz = coords_float.to(dev, torch.float64).contiguous()
+        N = int(xyz.shape[0])
+        K = int(instance_box.shape[0])
+        words = 1
+        while 32 * words < K:
+            words *= 2
+        if words > 8:
+            raise ValueError("more than 256 boxes in one scene")
+        boxes = instance_box.to(dev).float().contiguous()
+        vol = instance_box_volume.to(dev).float().contiguous()
+        cls = instance_cls.to(dev, torch.int64)
+        pt_off = np.array([0, N], dtype=np.int64)
+        spp_gid = torch.empty(N, dtype=torch.int32, device=dev)
+        perm = torch.empty(N, dtype=torch.int32, device=dev)
+        seg_off = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        spp_off = np.zeros(2, dtype=np.int32)
+        ws = self._workspace("densify", lib.gapro_densify_workspace_bytes(N, 1))
+        spp_raw = spp.to(dev, torch.int64).reshape(-1).contiguous()
+        _lib.check(lib.gapro_densify_spp(spp_raw.data_ptr(), pt_off.ctypes.data, 1, spp_gid.data_ptr(), perm.data_ptr(),
+                                         seg_off.data_ptr(), spp_off.ctypes.data, ws.data_ptr(), ws.numel(), stream),
+                   "gapro_densify_spp")
+        St = int(spp_off[-1])
+        spp_off_dev = self._dev(spp_off)
+        box_off_dev = self._dev(np.array([0, K], dtype=np.int32))
+        rule_id = {"volume": 0, "dist": 1, "none": 2}[rule]
+        inst_spp = torch.empty(St, dtype=torch.int32, device=dev)
+        inst_pt = torch.empty(N, dtype=torch.int32, device=dev)
+        thr = -1.0 if occ_thresh is None else float(np.float32(occ_thresh))
+        _lib.check(lib.gapro_heuristic_labels(xyz.data_ptr(), perm.data_ptr(), seg_off.data_ptr(), spp_off_dev.data_ptr(),
+                                              box_off_dev.data_ptr(), boxes.data_ptr(), vol.data_ptr(), 1, St, words,
+                                              rule_id, 1 if spp_align else 0, thr, inst_spp.data_ptr(),
+                                              inst_pt.data_ptr(), stream), "gapro_heuristic_labels")
+        if spp_align:
+            # per-superpoint semantics (gen_ps_utils.py:283-288 / :559-564), then the 128-bit broadcast kernel
+            sem_spp = torch.full((St,), -100, dtype=torch.int32, device=dev)
+            pos = inst_spp >= 0
+            sem_spp[pos] = cls[inst_spp[pos].long()].int()
+            sem_spp[inst_spp == -1] = int(instance_classes)
+            inst_out = torch.where(pos, inst_spp, torch.full_like(inst_spp, -100))
+            packed = torch.stack([sem_spp, inst_out, torch.ones_like(sem_spp).float().view(torch.int32),
+                                  torch.zeros_like(sem_spp)], dim=1).contiguous()
+            sem = torch.empty(N, dtype=torch.int32, device=dev)
+            inst = torch.empty(N, dtype=torch.int32, device=dev)
+            prob = torch.empty(N, dtype=torch.float32, device=dev)
+            _lib.check(lib.gapro_broadcast_labels(spp_gid.data_ptr(), N, packed.data_ptr(), sem.data_ptr(),
+                                                  inst.data_ptr(), prob.data_ptr(), stream), "gapro_broadcast_labels")
+            return sem, inst
+        sem = torch.full((N,), -100, dtype=torch.int32, device=dev)
+        inst = torch.full((N,), -100, dtype=torch.int32, device=dev)
+        pos = inst_pt >= 0
+        sem[pos] = cls[inst_pt[pos].long()].int()
+        sem[inst_pt == -1] = int(instance_classes)
+        inst[pos] = inst_pt[pos]
+        return sem, inst
+
     def _make_noise(self, scenes, region_scene, region_m, total):
         """Standard-normal draws for the variational-mean init (gpytorch draws them from the unseeded
         global RNG).  Seeded scenes: ONE numpy Generator per scene, regions consume it in event order."""

@@ -13,8 +13,9 @@ import torch
 from . import _lib
 from .engine import SceneInputs, get_engine
 
-__all__ = ["gen_pseudo_label_gaussian_process", "gen_pseudo_labels_batch", "getInstanceInfo", "batch_giou_cross",
-           "is_box1_in_box2", "is_within_bb_torch", "SceneInputs"]
+__all__ = ["gen_pseudo_label_gaussian_process", "gen_pseudo_labels_batch", "gen_pseudo_label_box2mask",
+           "gen_pseudo_label", "getInstanceInfo", "batch_giou_cross", "is_box1_in_box2", "is_within_bb_torch",
+           "SceneInputs"]
 
 
 def gen_pseudo_label_gaussian_process(
@@ -61,6 +62,30 @@ def gen_pseudo_labels_batch(scenes, instance_classes=18, ground_h=0.1, training_
     eng = get_engine(device)
     return eng.run(list(scenes), instance_classes=instance_classes, ground_h=ground_h, training_iter=training_iter,
                    thresh_spp_occu=thresh_spp_occu, jitter_zz=jitter_zz, debug=return_debug)
+
+
+def gen_pseudo_label_box2mask(coords_float, spp, instance_cls, instance_box, instance_box_volume,
+                              instance_classes=18, dataset_name="scannetv2"):
+    """Drop-in for gen_pseudo_label_box2mask (/root/reference/gapro/gen_ps_utils.py:242-290): points in
+    several boxes take the smallest one; for scannetv2 the labels are then aligned to superpoints by
+    majority vote (spp_align_label, :99-129).  Returns (ps_semantic_label[N] int32, ps_instance_label[N] int32)."""
+    eng = get_engine(coords_float.device if coords_float.is_cuda else None)
+    return eng.run_heuristic(coords_float, spp, instance_cls, instance_box, instance_box_volume,
+                             instance_classes=instance_classes, rule="volume",
+                             spp_align=(dataset_name == "scannetv2"), occ_thresh=None)
+
+
+def gen_pseudo_label(coords_float, spp, instance_cls, instance_box, instance_box_volume, instance_classes=18,
+                     dataset_name="scannetv2", heuristic_rule="volume"):
+    """Drop-in for gen_pseudo_label (/root/reference/gapro/gen_ps_utils.py:485-569): rule "volume", "dist" or
+    "none" for points in several boxes; for scannetv2 a majority vote per superpoint in which a box can only
+    win if it holds at least 70 % of the superpoint (:538-550)."""
+    if heuristic_rule not in ("volume", "dist", "none"):
+        raise Exception
+    eng = get_engine(coords_float.device if coords_float.is_cuda else None)
+    return eng.run_heuristic(coords_float, spp, instance_cls, instance_box, instance_box_volume,
+                             instance_classes=instance_classes, rule=heuristic_rule,
+                             spp_align=(dataset_name == "scannetv2"), occ_thresh=0.7)
 
 
 # --------------------------------------------------------------------------------------------

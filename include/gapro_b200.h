@@ -121,6 +121,24 @@ int gapro_occupancy(const double* xyz, const int32_t* perm, const int32_t* seg_o
                     int32_t* n_bbs, int32_t* cnt_in, int32_t* excl_cnt, int32_t* inter_cnt, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Heuristic labelers (the commented alternative at gen_ps.py:112-114).
+ * Replaces the arithmetic of gen_pseudo_label_box2mask (gen_ps_utils.py:242-290), gen_pseudo_label
+ * (:485-569) and spp_align_label (:99-129): per-point containment in the INSTANCE boxes (margins
+ * evaluated in float32, as there), rule for points in several boxes, majority vote per superpoint.
+ *   boxes      dev float[n_boxes,6], boxes_vol dev float[n_boxes]  (instance boxes only; box_off_dev
+ *              indexes them per scene)
+ *   rule       0 = smallest volume, 1 = nearest box centre, 2 = none (such points vote background)
+ *   spp_align  1: majority vote per superpoint -> inst_spp[S_total] (box index or -1);
+ *              0: per-point result -> inst_pt[n] (box index, -1 background, -2 undecided)
+ *   occ_thresh >= 0: only boxes holding >= occ_thresh of the superpoint may win the vote (0.7 in
+ *              gen_pseudo_label); < 0: no restriction (gen_pseudo_label_box2mask)
+ */
+int gapro_heuristic_labels(const double* xyz, const int32_t* perm, const int32_t* seg_off, const int32_t* spp_off_dev,
+                           const int32_t* box_off_dev, const float* boxes, const float* boxes_vol, int32_t n_scenes,
+                           int32_t s_total, int32_t words, int32_t rule, int32_t spp_align, float occ_thresh,
+                           int32_t* inst_spp, int32_t* inst_pt, void* stream);
+
+/* ---------------------------------------------------------------------------
  * B — superpoint feature pooling.  Replaces
  *     gp_feats_spp = torch_scatter.scatter(gp_feats, spp, dim=0, reduce="mean")   gen_ps_utils.py:357
  * float32 sum in increasing point index (torch_scatter CPU order, hence

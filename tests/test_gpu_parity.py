@@ -293,6 +293,29 @@ def test_full_size_scene_properties(engine, dev):
     assert (prob_spp[~gp] == 1).all() and np.isfinite(mu).all()
 
 
+@pytest.mark.parametrize("mode", ["box2mask", "volume", "dist", "none", "dist_pointwise", "none_pointwise"])
+def test_heuristic_labelers_bit_exact(dev, lib, mode):
+    """gen_pseudo_label_box2mask / gen_pseudo_label through the CUDA path vs the oracle."""
+    from gapro_b200.gen_ps_utils import gen_pseudo_label, gen_pseudo_label_box2mask
+    from oracle import heuristic_oracle as H
+    for name, seed in (("tiny", 2), ("small", 5)):
+        inp = synthetic_inputs(synthetic.make_scene(seed, name))
+        sc = to_scene_inputs(inp, dev)
+        args = (sc.coords_float, sc.spp, sc.instance_cls, sc.instance_box, sc.instance_box_volume)
+        oargs = (inp["xyz"], inp["spp"], inp["instance_cls"], inp["instance_box"].astype(np.float32),
+                 inp["instance_box_volume"].astype(np.float32))
+        if mode == "box2mask":
+            got = gen_pseudo_label_box2mask(*args)
+            ref = H.heuristic_labels(*oargs, box2mask=True)
+        else:
+            rule = mode.split("_")[0]
+            ds = "s3dis" if mode.endswith("pointwise") else "scannetv2"
+            got = gen_pseudo_label(*args, dataset_name=ds, heuristic_rule=rule)
+            ref = H.heuristic_labels(*oargs, dataset_name=ds, heuristic_rule=rule)
+        assert got[0].dtype == torch.int32 and got[1].dtype == torch.int32
+        assert (got[0].cpu().numpy() == ref[0]).all() and (got[1].cpu().numpy() == ref[1]).all()
+
+
 def test_saved_file_feeds_the_consumer_stub(engine, dev, tmp_path):
     from gapro_b200.gen_ps import save_pseudo_labels
     inp = synthetic_inputs(synthetic.make_scene(3, "tiny"))

@@ -186,3 +186,34 @@ def test_oracle_reproduces_golden_scene(name, seed, nseed):
     g = gold["mu"] != -100
     assert ((res[3] != -100) == g).all()
     assert rel_err(res[3][g], gold["mu"][g]) < 1e-5 and rel_err(res[4][g], gold["var"][g]) < 1e-5
+
+
+# ------------------------------------------------------------------------------- heuristic labelers (8f)
+def test_heuristic_labelers_known_answers():
+    from oracle import heuristic_oracle as H
+    # two overlapping boxes; superpoint 0 = points only in box 0, superpoint 1 = points in both,
+    # superpoint 2 = background
+    box = np.array([[0, 0, 0, 2, 2, 2], [1, 0, 0, 4, 2, 2]], np.float32)      # volumes 8 and 12
+    vol = np.prod(box[:, 3:] - box[:, :3], axis=1)
+    pts = np.array([[0.5, 1, 1], [0.6, 1, 1], [1.5, 1, 1], [1.2, 1, 1], [1.9, 1, 1], [9, 9, 9], [9.5, 9, 9]])
+    spp = np.array([10, 10, 20, 20, 20, 30, 30])
+    cls = np.array([3, 7])
+    sem, inst = H.heuristic_labels(pts, spp, cls, box, vol, box2mask=True)
+    assert inst.tolist() == [0, 0, 0, 0, 0, -100, -100] and sem.tolist() == [3, 3, 3, 3, 3, 18, 18]
+    sem, inst = H.heuristic_labels(pts, spp, cls, box, vol, heuristic_rule="dist")
+    # centres x = 1 and 2.5: 1.5 and 1.2 are nearer to box 0, 1.9 to box 1 -> majority box 0
+    assert inst.tolist() == [0, 0, 0, 0, 0, -100, -100]
+    sem, inst = H.heuristic_labels(pts, spp, cls, box, vol, heuristic_rule="none")
+    assert inst.tolist() == [0, 0, -100, -100, -100, -100, -100] and sem[2] == 18
+    sem, inst = H.heuristic_labels(pts, spp, cls, box, vol, heuristic_rule="none", dataset_name="s3dis")
+    assert inst.tolist() == [0, 0, -100, -100, -100, -100, -100] and sem[2] == -100 and sem[5] == 18
+    # margins are float32: a point exactly on float32(lo - 0.005) is inside
+    edge = float(np.float32(1.0) - np.float32(0.005))
+    occ = H.point_containment(np.array([[edge, 1, 1], [np.nextafter(edge, 0), 1, 1]]), box[1:])
+    assert occ[:, 0].tolist() == [True, False]
+    # the 70 % rule: a superpoint with 2 of 3 points in the box cannot take the box label
+    pts2 = np.array([[0.5, 1, 1], [0.6, 1, 1], [-3, 1, 1]])
+    sem, inst = H.heuristic_labels(pts2, np.zeros(3, int), cls[:1], box[:1], vol[:1], heuristic_rule="volume")
+    assert inst.tolist() == [-100, -100, -100]
+    sem, inst = H.heuristic_labels(pts2, np.zeros(3, int), cls[:1], box[:1], vol[:1], box2mask=True)
+    assert inst.tolist() == [0, 0, 0]
