@@ -328,6 +328,46 @@ def test_saved_file_feeds_the_consumer_stub(engine, dev, tmp_path):
     assert np.allclose(mu_label, gold["mu"], rtol=1e-4) and prob_label.shape == semantic_label.shape
 
 
+def test_cli_end_to_end_on_a_reference_shaped_dataset(dev, lib, tmp_path, monkeypatch):
+    """python -m gapro_b200.gen_ps on files laid out like dataset/scannetv2 (gen_ps.py:27-58): outputs
+    named <save_folder>/<scan>.pth, the 5-tuple contract, the resume rule, the oracle's labels."""
+    from gapro_b200 import gen_ps
+    from oracle import gen_ps_oracle as O
+    root = tmp_path / "dataset" / "scannetv2"
+    for sub in ("train", "superpoints", "scans_transform"):
+        (root / sub).mkdir(parents=True)
+    scans, inputs = ["scene0000_00", "scene0001_00", "scene0002_01"], {}
+    for i, scan in enumerate(scans):
+        sc = synthetic.make_scene(40 + i, "tiny")
+        torch.save((sc.xyz_raw, sc.rgb, sc.sem, sc.inst), str(root / "train" / f"{scan}_inst_nostuff.pth"))
+        torch.save(sc.spp, str(root / "superpoints" / f"{scan}.pth"))
+        (root / "scans_transform" / scan).mkdir()
+        (root / "scans_transform" / scan / f"{scan}.txt").write_text(
+            "axisAlignment = " + " ".join(repr(float(x)) for x in sc.axis_align.ravel()) + "\nnumColorFrames = 1\n")
+        inputs[scan] = gen_ps.prepare_inputs(sc.xyz_raw, sc.rgb, sc.sem, sc.inst, sc.spp, sc.axis_align)   # no planes json
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    # a result that already exists must be skipped (gen_ps.py:39-41)
+    save = tmp_path / "out"
+    save.mkdir()
+    torch.save(("sentinel",), str(save / "scene0001_00.pth"))
+    gen_ps.main(["--save_folder", str(save), "--seed", "7", "--batch_scenes", "2", "--eval_pslabel"])
+    assert torch.load(str(save / "scene0001_00.pth"), weights_only=False) == ("sentinel",)
+    import zlib
+    for scan in ("scene0000_00", "scene0002_01"):
+        sem, inst, prob, mu, var = torch.load(str(save / f"{scan}.pth"), weights_only=False)
+        inp = inputs[scan]
+        seed = (zlib.crc32(scan.encode()) ^ 7) & 0x7fffffff
+        ref = O.gen_pseudo_label_oracle(*oracle_args(inp), thresh_spp_occu=0.999, noise_seed=seed)
+        assert sem.dtype == np.int32 and inst.dtype == np.int32 and prob.dtype == np.float32
+        assert (sem == ref[0]).all() and (inst == ref[1]).all()
+        assert np.allclose(prob, ref[2], rtol=1e-5) and mu.shape == ref[3].shape
+        g = ref[3] != -100
+        assert np.allclose(mu[g], ref[3][g], rtol=1e-4, atol=0) and np.allclose(var[g], ref[4][g], rtol=1e-4, atol=0)
+
+
 def test_extension_is_the_code_that_ran(engine):
     """The CUDA library must be the thing that produced the numbers above."""
     assert os.path.samefile(_lib.LIB_PATH, os.path.join(os.path.dirname(_lib.__file__), "libgapro_b200.so"))
