@@ -427,18 +427,22 @@ k_build(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParam
     const int ti = t.y, tj = t.z;
     const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
     double* base = ws + R.base;
+    // row block [64][D] (read as broadcasts), column blocks transposed [D][65] (lanes read consecutive words)
+    constexpr int LDT = TB + 1;
     double* zi = smem_build;
-    double* zj = zi + TB * D;
-    double* xj = zj + TB * D;
+    double* zjT = zi + TB * D;
+    double* xjT = zjT + D * LDT;
     const double* Z = base + lay.Z;
     const double* Xc = prm.predict ? base + lay.Xt : base + lay.X;
     const int ncols = prm.predict ? R.N : R.M;       // valid columns of K_zx
     const int colrows = prm.predict ? R.Np : R.Mp;   // allocated rows of the column matrix
     const bool do_zz = (tj <= ti) && (tj < R.nb);
+    const bool have_x = (tj + 1) * TB <= colrows;
     for (int e = threadIdx.x; e < TB * D; e += blockDim.x) {
+        const int r = e / D, d = e - r * D;
         zi[e] = Z[(size_t)ti * TB * D + e];
-        zj[e] = do_zz ? Z[(size_t)tj * TB * D + e] : 0.0;
-        xj[e] = ((tj + 1) * TB <= colrows) ? Xc[(size_t)tj * TB * D + e] : 0.0;
+        zjT[d * LDT + r] = do_zz ? Z[(size_t)tj * TB * D + e] : 0.0;
+        xjT[d * LDT + r] = have_x ? Xc[(size_t)tj * TB * D + e] : 0.0;
     }
     __syncthreads();
     const double* sc = base + lay.scal;
@@ -447,24 +451,30 @@ k_build(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParam
     double* Kzx = base + lay.Kzx;
     double* Kzz = base + lay.L;
     double* Kc = base + lay.Kc;
-    for (int e = threadIdx.x; e < TB * TB; e += blockDim.x) {
-        const int li = e >> 6, lj = e & 63;
-        const int i = ti * TB + li, j = tj * TB + lj;
-        double d2 = 0.0;
-        for (int d = 0; d < D; ++d) {
-            const double df = zi[li * D + d] - xj[lj * D + d];
-            d2 += df * df;
+    // thread = (column lj, 16 rows): the column's features are read once per d and reused over the rows
+    const int lj = threadIdx.x & 63, lq = threadIdx.x >> 6;
+    const int j = tj * TB + lj;
+    double d2x[16], d2z[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) d2x[q] = d2z[q] = 0.0;
+    for (int d = 0; d < D; ++d) {
+        const double xv = xjT[d * LDT + lj], zv = zjT[d * LDT + lj];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const double zr = zi[(lq * 16 + q) * D + d];          // warp-uniform address: broadcast
+            const double a = zr - xv, b = zr - zv;
+            d2x[q] = fma(a, a, d2x[q]);
+            d2z[q] = fma(b, b, d2z[q]);
         }
-        Kzx[(size_t)i * R.Wp + j] = (i < R.M && j < ncols) ? s * exp(-0.5 * (d2 * inv_l2)) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int i = ti * TB + lq * 16 + q;
+        Kzx[(size_t)i * R.Wp + j] = (i < R.M && j < ncols) ? s * exp(-0.5 * (d2x[q] * inv_l2)) : 0.0;
         if (do_zz) {
-            double q2 = 0.0;
-            for (int d = 0; d < D; ++d) {
-                const double df = zi[li * D + d] - zj[lj * D + d];
-                q2 += df * df;
-            }
             double v, v0 = 0.0;
             if (i < R.M && j < R.M) {
-                v0 = s * exp(-0.5 * (q2 * inv_l2));
+                v0 = s * exp(-0.5 * (d2z[q] * inv_l2));
                 v = v0 + (i == j ? prm.jitter_zz : 0.0);
             } else {
                 v = (i == j) ? 1.0 : 0.0;
@@ -902,36 +912,39 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
         __syncthreads();
         const int j = jb + lane;
         if (j < R.M) {
-            double zj[DMAX], xj[DMAX];
-#pragma unroll
-            for (int d = 0; d < DMAX; ++d) {
-                zj[d] = d < D ? Zs[d][lane] : 0.0;
-                xj[d] = d < D ? Xs[d][lane] : 0.0;
-            }
+            // the adjoint weights do not depend on the distances: read them first, then ONE pass over d
+            double grz2[ROWS], grx[ROWS], d2z[ROWS], d2x[ROWS];
 #pragma unroll
             for (int q = 0; q < ROWS; ++q) {
-                const int rr = warp * ROWS + q, i = row0 + rr;
+                const int i = row0 + warp * ROWS + q;
+                grz2[q] = grx[q] = d2z[q] = d2x[q] = 0.0;
                 if (i < R.M) {
                     const double gk = base[lay.Bm + (size_t)i * R.Wp + j], kz = base[lay.Kc + (size_t)i * R.Mp + j];
                     const double gc = base[lay.GC + (size_t)i * R.Mp + j], kx = base[lay.Kzx + (size_t)i * R.Wp + j];
-                    double d2z = 0.0, d2x = 0.0;
-#pragma unroll
-                    for (int d = 0; d < DMAX; ++d) {
-                        const double zi = Zi[rr][d];
-                        const double dz = zi - zj[d], dx = zi - xj[d];
-                        d2z = fma(dz, dz, d2z);
-                        d2x = fma(dx, dx, d2x);
-                    }
                     // zz: W = Gr + Gr^T = 2 Gr (G_K, K_zz symmetric);  zx: Gr once.
                     // sum_j [2 grz (z_i - z_j) + grx (z_i - x_j)] = z_i * cz - sum_j (2 grz z_j + grx x_j)
-                    const double grz2 = -gk * kz, grx = -0.5 * gc * kx;
+                    grz2[q] = -gk * kz;
+                    grx[q] = -0.5 * gc * kx;
                     as[q] += (gk * kz + gc * kx) * inv_s;
-                    al[q] += (0.5 * grz2 * d2z + grx * d2x) * (inv_l2 * m2_ell);
-                    cz[q] += grz2 + grx;
-#pragma unroll
-                    for (int d = 0; d < DMAX; ++d) az[q][d] = fma(-grz2, zj[d], fma(-grx, xj[d], az[q][d]));
+                    cz[q] += grz2[q] + grx[q];
                 }
             }
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d) {
+                if (d < D) {
+                    const double zjd = Zs[d][lane], xjd = Xs[d][lane];
+#pragma unroll
+                    for (int q = 0; q < ROWS; ++q) {
+                        const double zi = Zi[warp * ROWS + q][d];
+                        const double dz = zi - zjd, dx = zi - xjd;
+                        d2z[q] = fma(dz, dz, d2z[q]);
+                        d2x[q] = fma(dx, dx, d2x[q]);
+                        az[q][d] = fma(-grz2[q], zjd, fma(-grx[q], xjd, az[q][d]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < ROWS; ++q) al[q] += (0.5 * grz2[q] * d2z[q] + grx[q] * d2x[q]) * (inv_l2 * m2_ell);
         }
     }
 #pragma unroll
@@ -1202,7 +1215,7 @@ struct Driver {
     void build(const GpParams& p) {
         const int4* tiles = p.predict ? tb.wide : tb.full;
         const int n = p.predict ? tb.n_wide : tb.n_full;
-        k_build<<<n, 256, 3 * TB * D * sizeof(double), stream>>>(tb.regs, tiles, p, ws);
+        k_build<<<n, 256, (TB * D + 2 * D * (TB + 1)) * sizeof(double), stream>>>(tb.regs, tiles, p, ws);
         ++g_launches;
     }
 
@@ -1230,7 +1243,7 @@ struct Driver {
         if (D <= 8)
             k_kgrad<8, 4><<<tb.n_rows * 2, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         else if (D <= 32)
-            k_kgrad<32, 1><<<tb.n_rows * 8, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad<32, 2><<<tb.n_rows * 4, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         else
             k_kgrad<64, 1><<<tb.n_rows * 8, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         ++g_launches;
@@ -1451,7 +1464,7 @@ static int allow_smem(K kernel, int bytes) {
 static int set_kernel_attributes() {
     static bool done = false;
     if (done) return GAPRO_OK;
-    int rc = allow_smem(k_build, 3 * TB * 64 * 8);
+    int rc = allow_smem(k_build, (TB * 64 + 2 * 64 * (TB + 1)) * 8);
     if (rc == GAPRO_OK) rc = allow_smem(k_rl_diag, DIAG_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_rl_panel, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_rl_update, GEMM_SMEM);
@@ -1469,7 +1482,7 @@ static int set_kernel_attributes() {
         if (rc == GAPRO_OK) rc = allow_smem(k_colstats, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_grad_m, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<8, 4>, 0);
-        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<32, 1>, 0);
+        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<32, 2>, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<64, 1>, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_adam_small, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_region_init, 0);
