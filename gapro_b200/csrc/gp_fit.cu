@@ -968,6 +968,101 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
     }
 }
 
+// Wide-feature variant (8 < D <= 64, e.g. the 32-d deep features of --use_deepfeat): lanes run over the
+// feature DIMENSION for the inducing-point gradient (no per-lane D-vector, no warp reduction over d)
+// and over the columns for the scalar sums.  The squared distance is recovered from the stored kernel
+// value, r^2 = -2 ln(K / s), so the D-wide difference is never formed.  One warp owns 8 rows.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+k_kgrad_wide(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpParams prm, double* __restrict__ ws) {
+    constexpr int DP = 32 * NCH;
+    __shared__ double Zs[32][DP];
+    __shared__ double Xs[32][DP];
+    const int2 rt = rtiles[blockIdx.x];
+    const Region R = regs[rt.x];
+    const int D = prm.D;
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
+    double* base = ws + R.base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* sc = base + lay.scal;
+    const double ell = softplus_d(sc[SC_RL]), s = softplus_d(sc[SC_RS]);
+    const double inv_l2 = 1.0 / (ell * ell), inv_s = 1.0 / s, m2_ell = -2.0 / ell;
+    const double* Z = base + lay.Z;
+    const double* X = base + lay.X;
+    const int row0 = rt.y * TB + warp * 8;
+    double az[8][NCH], as[8], al[8], cz[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        as[q] = al[q] = cz[q] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) az[q][c] = 0.0;
+    }
+    for (int jb = 0; jb < R.M; jb += 32) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * DP; e += blockDim.x) {
+            const int jj = e / DP, d = e - jj * DP;
+            const bool ok = (jb + jj < R.M) && d < D;
+            Zs[jj][d] = ok ? Z[(size_t)(jb + jj) * D + d] : 0.0;
+            Xs[jj][d] = ok ? X[(size_t)(jb + jj) * D + d] : 0.0;
+        }
+        __syncthreads();
+        const int j = jb + lane;
+        double grz2[8], grx[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i = row0 + q;
+            grz2[q] = grx[q] = 0.0;
+            if (i < R.M && j < R.M) {
+                const double gk = base[lay.Bm + (size_t)i * R.Wp + j], kz = base[lay.Kc + (size_t)i * R.Mp + j];
+                const double gc = base[lay.GC + (size_t)i * R.Mp + j], kx = base[lay.Kzx + (size_t)i * R.Wp + j];
+                grz2[q] = -gk * kz;
+                grx[q] = -0.5 * gc * kx;
+                as[q] += (gk * kz + gc * kx) * inv_s;
+                cz[q] += grz2[q] + grx[q];
+                const double r2z = kz > 0.0 ? -2.0 * log(kz * inv_s) : 0.0;     // r^2 (already divided by l^2)
+                const double r2x = kx > 0.0 ? -2.0 * log(kx * inv_s) : 0.0;
+                al[q] += (0.5 * grz2[q] * r2z + grx[q] * r2x) * m2_ell;
+            }
+        }
+#pragma unroll 4
+        for (int jj = 0; jj < 32; ++jj) {
+            double zv[NCH], xv[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                zv[c] = Zs[jj][lane + 32 * c];
+                xv[c] = Xs[jj][lane + 32 * c];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const double gz = __shfl_sync(0xffffffffu, grz2[q], jj), gx = __shfl_sync(0xffffffffu, grx[q], jj);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) az[q][c] = fma(-gz, zv[c], fma(-gx, xv[c], az[q][c]));
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int i = row0 + q;
+        double a0 = as[q], a1 = al[q], a2 = cz[q];
+        for (int o = 16; o; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (i < R.M) {
+            if (lane == 0) {
+                base[lay.gsrow + i] = a0;
+                base[lay.glrow + i] = a1;
+            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int d = lane + 32 * c;
+                if (d < D) base[lay.gZ + (size_t)i * D + d] = 2.0 * inv_l2 * fma(a2, Z[(size_t)i * D + d], az[q][c]);
+            }
+        }
+    }
+}
+
 // Adam on Z and on the three scalars (c, rho_s, rho_l).  One CTA per region.
 __device__ double block_sum(double v, double* red) {
     const int tid = threadIdx.x;
@@ -1243,9 +1338,9 @@ struct Driver {
         if (D <= 8)
             k_kgrad<8, 4><<<tb.n_rows * 2, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         else if (D <= 32)
-            k_kgrad<32, 2><<<tb.n_rows * 4, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad_wide<1><<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         else
-            k_kgrad<64, 1><<<tb.n_rows * 8, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad_wide<2><<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         ++g_launches;
     }
 
@@ -1482,8 +1577,8 @@ static int set_kernel_attributes() {
         if (rc == GAPRO_OK) rc = allow_smem(k_colstats, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_grad_m, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<8, 4>, 0);
-        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<32, 2>, 0);
-        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<64, 1>, 0);
+        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad_wide<1>, 0);
+        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad_wide<2>, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_adam_small, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_region_init, 0);
     }
