@@ -352,21 +352,6 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
             *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = o;
         })
     } else if (PH == PH_GT) {  // dT = tril(2 A diag(g_v) B^T + (T - diag(1/T_ii))/N), Adam on T
-        {   // the epilogue reads and rewrites T and its two Adam moments: start pulling them towards L2 now
-            const double* T0 = base + lay.T;
-            const double* T1 = base + lay.Tm;
-            const double* T2 = base + lay.Tv;
-            ACC_FOREACH(true, true, r0, c0, {
-                (void)v0;
-                (void)v1;
-                if (row < R.M && col <= row) {
-                    const size_t idx = (size_t)row * Mp + col;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(T0 + idx));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(T1 + idx));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(T2 + idx));
-                }
-            })
-        }
         gemm_accum<true, true>(acc, base + lay.A + (size_t)r0 * Wp, Wp, base + lay.Bm + (size_t)c0 * Wp, Wp, 0, kend,
                                base + lay.gv, sm, mlim, nlim);
         double* T = base + lay.T;
@@ -927,24 +912,21 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
         __syncthreads();
         const int j = jb + lane;
         if (j < R.M) {
-            // zz: W = Gr + Gr^T = 2 Gr (G_K, K_zz symmetric);  zx: Gr once.
-            // sum_j [2 grz (z_i - z_j) + grx (z_i - x_j)] = z_i * cz - sum_j (2 grz z_j + grx x_j);
-            // r^2 is recovered from the stored kernel value (r^2 = -2 ln(K/s)), no D-wide difference needed
-            double grz2[ROWS], grx[ROWS];
+            // the adjoint weights do not depend on the distances: read them first, then ONE pass over d
+            double grz2[ROWS], grx[ROWS], d2z[ROWS], d2x[ROWS];
 #pragma unroll
             for (int q = 0; q < ROWS; ++q) {
                 const int i = row0 + warp * ROWS + q;
-                grz2[q] = grx[q] = 0.0;
+                grz2[q] = grx[q] = d2z[q] = d2x[q] = 0.0;
                 if (i < R.M) {
                     const double gk = base[lay.Bm + (size_t)i * R.Wp + j], kz = base[lay.Kc + (size_t)i * R.Mp + j];
                     const double gc = base[lay.GC + (size_t)i * R.Mp + j], kx = base[lay.Kzx + (size_t)i * R.Wp + j];
+                    // zz: W = Gr + Gr^T = 2 Gr (G_K, K_zz symmetric);  zx: Gr once.
+                    // sum_j [2 grz (z_i - z_j) + grx (z_i - x_j)] = z_i * cz - sum_j (2 grz z_j + grx x_j)
                     grz2[q] = -gk * kz;
                     grx[q] = -0.5 * gc * kx;
                     as[q] += (gk * kz + gc * kx) * inv_s;
                     cz[q] += grz2[q] + grx[q];
-                    const double r2z = kz > 0.0 ? -2.0 * log(kz * inv_s) : 0.0;
-                    const double r2x = kx > 0.0 ? -2.0 * log(kx * inv_s) : 0.0;
-                    al[q] += (0.5 * grz2[q] * r2z + grx[q] * r2x) * m2_ell;
                 }
             }
 #pragma unroll
@@ -952,9 +934,17 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
                 if (d < D) {
                     const double zjd = Zs[d][lane], xjd = Xs[d][lane];
 #pragma unroll
-                    for (int q = 0; q < ROWS; ++q) az[q][d] = fma(-grz2[q], zjd, fma(-grx[q], xjd, az[q][d]));
+                    for (int q = 0; q < ROWS; ++q) {
+                        const double zi = Zi[warp * ROWS + q][d];
+                        const double dz = zi - zjd, dx = zi - xjd;
+                        d2z[q] = fma(dz, dz, d2z[q]);
+                        d2x[q] = fma(dx, dx, d2x[q]);
+                        az[q][d] = fma(-grz2[q], zjd, fma(-grx[q], xjd, az[q][d]));
+                    }
                 }
             }
+#pragma unroll
+            for (int q = 0; q < ROWS; ++q) al[q] += (0.5 * grz2[q] * d2z[q] + grx[q] * d2x[q]) * (inv_l2 * m2_ell);
         }
     }
 #pragma unroll
