@@ -79,6 +79,32 @@ def test_stages_bit_exact_against_oracle(engine, dev, names):
         p0 += n
 
 
+def test_stages_with_more_than_32_boxes_and_many_scenes(engine, dev):
+    """Two 32-bit occupancy words per superpoint (44 boxes) and a batch of 40 scenes (scene lookup loops)."""
+    from oracle import gen_ps_oracle as O
+    cfg = synthetic.SceneConfig(n_points=30_000, n_objects=40, s_target=900, overlap=0.5, n_nested=3)
+    inps = [synthetic_inputs(synthetic.make_scene(61, cfg))]
+    inps += [synthetic_inputs(synthetic.make_scene(70 + i, "tiny")) for i in range(39)]
+    scenes = [to_scene_inputs(inp, dev, noise_seed=i) for i, inp in enumerate(inps)]
+    outs, dbg = engine.run(scenes, thresh_spp_occu=0.999, training_iter=1, debug=True, want_cnt_in=True)
+    assert dbg.occ_bits.shape[1] == 2
+    p0 = 0
+    for i, inp in enumerate(inps):
+        if i in (0, 1, 17, 39):
+            _, od = O.gen_pseudo_label_oracle(*oracle_args(inp), thresh_spp_occu=0.999, fit_fn=fake_fit, noise_seed=i,
+                                              return_debug=True)
+            s0, s1 = dbg.spp_off[i], dbg.spp_off[i + 1]
+            B = dbg.box_off[i + 1] - dbg.box_off[i]
+            n = len(inp["xyz"])
+            assert (dbg.spp_gid.cpu().numpy()[p0:p0 + n] - s0 == od["spp_dense"]).all()
+            assert (dbg.cnt_in.cpu().numpy()[s0:s1, :B] == od["cnt_in"]).all()
+            assert (unpack_bits(dbg.occ_bits[s0:s1], B) == od["occ_spp"]).all()
+            assert (dbg.feats_spp.cpu().numpy()[s0:s1].view(np.uint32) == od["feats_spp"].view(np.uint32)).all()
+            kinds = {0: "nest", 1: "nest", 2: "gp"}
+            assert [(kinds[k], a, b) for k, a, b in dbg.events[i]] == [(e[0], e[1], e[2]) for e in od["events"]]
+        p0 += len(inp["xyz"])
+
+
 def test_containment_edges_and_ragged_superpoints(engine, dev):
     """Points exactly on lo-0.005 / hi+0.005, a 1-point superpoint, a 3000-point superpoint, raw ids
     with negative values and a huge offset."""
@@ -186,6 +212,22 @@ def test_gp_batching_and_chunking_do_not_change_results(dev, lib):
     _, chunked = _fit_cases(dev, idx, workspace_bytes=1)          # forces one region per chunk
     for a, b in zip(together, chunked):
         assert torch.equal(a[5], b[5]) and torch.equal(a[6], b[6])
+
+
+def test_gp_more_test_rows_than_training_rows(dev, lib):
+    """N_test >> M: the column-wide buffers are wider than the training block (Wp > Mp)."""
+    from gapro_b200.gaussian_process_utils import fit_gp_regions
+    from oracle import gp_oracle as G
+    rng = np.random.default_rng(11)
+    X = rng.normal(size=(20, 6)).astype(np.float32)
+    X[10:] += 1.0
+    Xt = (rng.normal(size=(200, 6)) * 1.5).astype(np.float32)
+    nz = rng.standard_normal(20).astype(np.float32)
+    feats = torch.from_numpy(np.concatenate([X, Xt])).to(dev)
+    res = fit_gp_regions(feats, [np.arange(20)], [10], [np.arange(20, 220)], init_noise=[nz], return_float64=True)[0]
+    o = G.fit_region_autograd(X, 10, Xt, nz)
+    assert rel_err(res[5].cpu().numpy(), o["mu64"]) < TOL and rel_err(res[6].cpu().numpy(), o["var64"]) < TOL
+    assert (res[2].cpu().numpy() == o["label"])[np.abs(o["prob64"] - 0.5) > EPS].all()
 
 
 def test_gp_degenerate_regions(dev, lib):
