@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["fit_gp_spp", "fit_gp_regions"]
+__all__ = ["fit_gp_spp", "fit_gp", "fit_gp_regions"]
 
 
 def fit_gp_regions(feats_spp, train_lists, n_b1, test_lists, init_noise=None, training_iter=50, lr=0.1,
@@ -104,3 +104,59 @@ def fit_gp_spp(coords_float_spp, feats_spp, b1_inds, b2_inds, intersect_inds, tr
     res = fit_gp_regions(feats_spp, [train], [int(b1.numel())], [intersect_inds],
                          init_noise=None if init_noise is None else [init_noise], training_iter=training_iter)
     return res[0]
+
+
+def _pool_by_superpoint(feats_rows, spp_rows):
+    """scatter-mean of `feats_rows` over unique(spp_rows) in sorted-id order, index-ordered float32 sums
+    (gapro_densify_spp + gapro_pool_feats): what gaussian_process_utils.py:66-70 does with torch_scatter."""
+    lib = _lib.load()
+    dev = feats_rows.device
+    n, D = int(feats_rows.shape[0]), int(feats_rows.shape[1])
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    raw = spp_rows.to(dev, torch.int64).contiguous()
+    pt_off = np.array([0, n], dtype=np.int64)
+    gid = torch.empty(n, dtype=torch.int32, device=dev)
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    seg = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    spp_off = np.zeros(2, dtype=np.int32)
+    ws = torch.empty(lib.gapro_densify_workspace_bytes(n, 1), dtype=torch.uint8, device=dev)
+    _lib.check(lib.gapro_densify_spp(raw.data_ptr(), pt_off.ctypes.data, 1, gid.data_ptr(), perm.data_ptr(),
+                                     seg.data_ptr(), spp_off.ctypes.data, ws.data_ptr(), ws.numel(), stream),
+               "gapro_densify_spp")
+    S = int(spp_off[1])
+    out = torch.empty((S, D), dtype=torch.float32, device=dev)
+    src = feats_rows.float().contiguous()
+    _lib.check(lib.gapro_pool_feats(src.data_ptr(), perm.data_ptr(), seg.data_ptr(), S, D, out.data_ptr(), stream),
+               "gapro_pool_feats")
+    return out
+
+
+def fit_gp(coords_float, feats, spp, b1_inds, b2_inds, intersect_inds, training_iter=50, npoint_nearest=800,
+           spp_pool=True, *, init_noise=None):
+    """Drop-in for the point-level variant fit_gp (/root/reference/gapro/gaussian_process_utils.py:28-116):
+    training rows are the superpoint means of the points of each box (spp_pool=True) or the
+    `npoint_nearest` points closest to the centroid of the intersection (spp_pool=False); prediction is
+    per intersection POINT.  Returns (pred_probs, pred_probs_new, pred_labels, pred_variance) with
+    pred_variance the Bernoulli variance p(1-p), as there (:110)."""
+    if not feats.is_cuda:
+        raise _lib.GaproError("fit_gp needs CUDA tensors; gapro_b200 has no CPU fallback")
+    feats = feats.float()
+    b1_feats, b2_feats = feats[b1_inds], feats[b2_inds]
+    if spp_pool:
+        b1_feats = _pool_by_superpoint(b1_feats, spp[b1_inds])
+        b2_feats = _pool_by_superpoint(b2_feats, spp[b2_inds])
+    else:
+        centroid = coords_float[intersect_inds].mean(0)
+        if len(b1_inds) > npoint_nearest:
+            d = ((coords_float[b1_inds] - centroid[None, :]) ** 2).sum(1)
+            b1_feats = b1_feats[torch.topk(d, k=npoint_nearest, largest=False)[1]]
+        if len(b2_inds) > npoint_nearest:
+            d = ((coords_float[b2_inds] - centroid[None, :]) ** 2).sum(1)
+            b2_feats = b2_feats[torch.topk(d, k=npoint_nearest, largest=False)[1]]
+    n1, n2 = int(b1_feats.shape[0]), int(b2_feats.shape[0])
+    test = feats[intersect_inds]
+    table = torch.cat([b1_feats, b2_feats, test], 0).contiguous()
+    res = fit_gp_regions(table, [np.arange(n1 + n2)], [n1], [np.arange(n1 + n2, n1 + n2 + int(test.shape[0]))],
+                         init_noise=None if init_noise is None else [init_noise], training_iter=training_iter)[0]
+    probs, conf, labels = res[0], res[1], res[2]
+    return probs, conf, labels, probs * (1 - probs)

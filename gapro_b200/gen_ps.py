@@ -90,6 +90,19 @@ def synthetic_inputs(scene, use_deepfeat=False) -> dict:
                           deep_feats=scene.deep_feats if use_deepfeat else None)
 
 
+def load_scene(filename, scan_name, use_deepfeat=False, deepfeat_folder=None, data_root=DATA_ROOT):
+    """Disk -> host arrays for one scene (gen_ps.py:45-77): scene tuple, superpoints, optional deep
+    features, axis alignment, instance boxes, optional wall boxes.  Returns (inputs, sem, inst)."""
+    from .scannet_planes import get_wall_boxes
+    xyz, rgb, sem, inst = torch.load(filename, weights_only=False)
+    spp = torch.load(osp.join(data_root, "superpoints", scan_name + ".pth"), weights_only=False)
+    deep = torch.load(osp.join(deepfeat_folder, scan_name + ".pth"), weights_only=False) if use_deepfeat else None
+    A = read_axis_align_matrix(osp.join(data_root, "scans_transform", scan_name, scan_name + ".txt"))
+    _, wall_box, wall_vol = get_wall_boxes(scan_name, planes_root=osp.join(data_root, "scannet_planes"),
+                                           transform_root=osp.join(data_root, "scans_transform"))
+    return prepare_inputs(xyz, rgb, sem, inst, spp, A, wall_box, wall_vol, deep), sem, inst
+
+
 def save_pseudo_labels(path, result, per_point_uncertainty=False, spp_dense=None):
     """torch.save of the 5-tuple of numpy arrays (gen_ps.py:126-132).  The reference saves mu/var
     per SUPERPOINT although its consumers index them per point (SURVEY.md Q1);
@@ -119,6 +132,7 @@ def main(argv=None):
     # additions
     parser.add_argument("--batch_scenes", type=int, default=8, help="scenes per GPU pass")
     parser.add_argument("--seed", type=int, default=None, help="seed of the GP initialisation noise")
+    parser.add_argument("--load_workers", type=int, default=8, help="host threads reading / preparing the next batch")
     parser.add_argument("--per_point_uncertainty", action="store_true",
                         help="save mu/var broadcast to points (what the ISBNet/SPFormer loaders index)")
     args = parser.parse_args(argv)
@@ -140,20 +154,23 @@ def main(argv=None):
     todo = shard_scenes(todo, rank, world)
 
     from .eval_ps_labels import get_miou_scene
-    from .scannet_planes import get_wall_boxes
     ious, meta = [], []
     t0 = time.time()
-    for i in range(0, len(todo), args.batch_scenes):
-        chunk, scenes, gts = todo[i:i + args.batch_scenes], [], []
-        for fn, scan in chunk:
-            xyz, rgb, sem, inst = torch.load(fn, weights_only=False)
-            spp = torch.load(osp.join(DATA_ROOT, "superpoints", scan + ".pth"), weights_only=False)
-            deep = torch.load(osp.join(args.deepfeat_folder, scan + ".pth"), weights_only=False) if args.use_deepfeat else None
-            A = read_axis_align_matrix(osp.join(DATA_ROOT, "scans_transform", scan, scan + ".txt"))
-            _, wall_box, wall_vol = get_wall_boxes(scan)
-            inp = prepare_inputs(xyz, rgb, sem, inst, spp, A, wall_box, wall_vol, deep)
+    chunks = [todo[i:i + args.batch_scenes] for i in range(0, len(todo), args.batch_scenes)]
+    # host side of the NEXT batch (disk reads, alignment, boxes) runs on worker threads while the GPU
+    # works on the current one
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=max(1, min(args.load_workers, args.batch_scenes)))
+    submit = lambda chunk: [pool.submit(load_scene, fn, scan, args.use_deepfeat, args.deepfeat_folder)
+                            for fn, scan in chunk]
+    pending = submit(chunks[0]) if chunks else []
+    for ci, chunk in enumerate(chunks):
+        loaded = [f.result() for f in pending]
+        pending = submit(chunks[ci + 1]) if ci + 1 < len(chunks) else []
+        scenes, gts = [], []
+        for (fn, scan), (inp, sem, inst) in zip(chunk, loaded):
             seed = None if args.seed is None else (zlib.crc32(scan.encode()) ^ args.seed) & 0x7fffffff
-            scenes.append(to_scene_inputs(inp, device, noise_seed=seed))
+            scenes.append(to_scene_inputs(inp, device, noise_seed=seed, pin=True))
             gts.append((sem, inst))
         results = gen_pseudo_labels_batch(scenes, instance_classes=18, ground_h=0.1, training_iter=50,
                                           thresh_spp_occu=0.999, device=device)    # gen_ps.py:106-110

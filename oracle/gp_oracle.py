@@ -290,3 +290,31 @@ def fit_region_manual(train_x, n_b1, test_x, init_noise, iters=50, lr=0.1,
     if return_params:
         out["params"] = [np.asarray(p, dtype=np.float64) for p in params]
     return out
+
+
+def fit_gp_points_oracle(coords_float, feats, spp, b1_inds, b2_inds, intersect_inds, init_noise, training_iter=50,
+                         npoint_nearest=800, spp_pool=True):
+    """Restates the point-level variant fit_gp (/root/reference/gapro/gaussian_process_utils.py:28-116)
+    on top of fit_region_autograd (fp64 policy).  Returns (probs, conf, labels, bernoulli_variance)."""
+    from .gen_ps_oracle import scatter_sum_index_order
+    coords = np.asarray(coords_float, dtype=np.float64)
+    feats = np.asarray(feats, dtype=np.float32)
+    spp = np.asarray(spp)
+
+    def pooled(idx):
+        _, dense = np.unique(spp[idx], return_inverse=True)
+        dense = dense.reshape(-1)
+        s, cnt = scatter_sum_index_order(feats[idx], dense, int(dense.max()) + 1)
+        return s / np.maximum(cnt, 1).astype(np.float32)[:, None]
+
+    def nearest(idx):
+        if len(idx) <= npoint_nearest:
+            return feats[idx]
+        c = coords[intersect_inds].mean(0)
+        d = ((coords[idx] - c[None, :]) ** 2).sum(1)
+        return feats[idx][np.argsort(d, kind="stable")[:npoint_nearest]]
+
+    f1, f2 = (pooled(b1_inds), pooled(b2_inds)) if spp_pool else (nearest(b1_inds), nearest(b2_inds))
+    r = fit_region_autograd(np.concatenate([f1, f2]), len(f1), feats[intersect_inds], init_noise, iters=training_iter)
+    p = r["prob"]
+    return p, r["conf"], r["label"], (p * (np.float32(1.0) - p)).astype(np.float32)

@@ -230,6 +230,35 @@ def test_gp_more_test_rows_than_training_rows(dev, lib):
     assert (res[2].cpu().numpy() == o["label"])[np.abs(o["prob64"] - 0.5) > EPS].all()
 
 
+@pytest.mark.parametrize("spp_pool", [True, False])
+def test_point_level_fit_gp_variant(dev, lib, spp_pool):
+    """fit_gp (gaussian_process_utils.py:28-116) on points of a synthetic scene."""
+    from gapro_b200.gaussian_process_utils import fit_gp
+    from oracle import gp_oracle as G
+    inp = synthetic_inputs(synthetic.make_scene(12, "tiny"))
+    rng = np.random.default_rng(4)
+    N = len(inp["xyz"])
+    order = rng.permutation(N)
+    b1, b2, inter = np.sort(order[:900]), np.sort(order[900:1500]), np.sort(order[1500:1540])
+    feats = inp["mask_feats"].astype(np.float32)
+    # spp_pool=False keeps the 150 points nearest to the intersection centroid
+    kw = dict(npoint_nearest=150, spp_pool=spp_pool)
+    if spp_pool:
+        n_train = len(np.unique(inp["spp"][b1])) + len(np.unique(inp["spp"][b2]))
+    else:
+        n_train = 300
+    nz = rng.standard_normal(n_train).astype(np.float32)
+    ref = G.fit_gp_points_oracle(inp["xyz"], feats, inp["spp"], b1, b2, inter, nz, **kw)
+    T = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+    got = fit_gp(T(inp["xyz"], torch.float64), T(feats, torch.float32), T(inp["spp"], torch.int64), T(b1, torch.int64),
+                 T(b2, torch.int64), T(inter, torch.int64), init_noise=nz, **kw)
+    assert len(got) == 4 and all(len(t) == len(inter) for t in got)
+    assert np.allclose(got[0].cpu().numpy(), ref[0], rtol=1e-4, atol=1e-7)
+    assert np.allclose(got[3].cpu().numpy(), ref[3], rtol=1e-4, atol=1e-7)
+    sure = np.abs(ref[0].astype(np.float64) - 0.5) > 1e-5
+    assert (got[2].cpu().numpy()[sure] == ref[2][sure]).all()
+
+
 def test_gp_degenerate_regions(dev, lib):
     from gapro_b200.gaussian_process_utils import fit_gp_regions, fit_gp_spp
     from oracle import gp_oracle as G

@@ -47,6 +47,25 @@ def test_axis_align_reader(tmp_path):
     assert (gen_ps.read_axis_align_matrix(str(f)) == A).all()
 
 
+def test_load_scene_reads_the_reference_layout(tmp_path):
+    """dataset/scannetv2/{train,superpoints,scans_transform} as gen_ps.py:27-69 expects them."""
+    root = tmp_path / "dataset" / "scannetv2"
+    for sub in ("train", "superpoints", "scans_transform/scene0000_00"):
+        (root / sub).mkdir(parents=True)
+    sc = synthetic.make_scene(9, "tiny")
+    fn = str(root / "train" / "scene0000_00_inst_nostuff.pth")
+    torch.save((sc.xyz_raw, sc.rgb, sc.sem, sc.inst), fn)
+    torch.save(sc.spp, str(root / "superpoints" / "scene0000_00.pth"))
+    (root / "scans_transform" / "scene0000_00" / "scene0000_00.txt").write_text(
+        "axisAlignment = " + " ".join(repr(float(x)) for x in sc.axis_align.ravel()) + "\n")
+    inp, sem, inst = gen_ps.load_scene(fn, "scene0000_00", data_root=str(root))
+    ref = gen_ps.prepare_inputs(sc.xyz_raw, sc.rgb, sc.sem, sc.inst, sc.spp, sc.axis_align)
+    for k in ("xyz", "mask_feats", "spp", "instance_cls", "instance_box", "instance_box_volume"):
+        assert (np.asarray(inp[k]) == np.asarray(ref[k])).all(), k
+    assert len(inp["wall_box"]) == 0 and (sem == sc.sem).all() and (inst == sc.inst).all()
+    assert os.path.basename(fn)[:12] == "scene0000_00"
+
+
 def test_saved_file_contract_roundtrip(tmp_path):
     """What ISBNet/isbnet/data/scannetv2.py:46-48 and SPFormer/spformer/dataset/scannetv2.py:275-277 do."""
     N, S = 1000, 40
