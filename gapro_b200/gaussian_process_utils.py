@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["fit_gp_spp", "fit_gp", "fit_gp_regions"]
+__all__ = ["fit_gp_spp", "fit_gp", "fit_gp_ensemble", "fit_gp_regions"]
 
 
 def fit_gp_regions(feats_spp, train_lists, n_b1, test_lists, init_noise=None, training_iter=50, lr=0.1,
@@ -106,7 +106,7 @@ def fit_gp_spp(coords_float_spp, feats_spp, b1_inds, b2_inds, intersect_inds, tr
     return res[0]
 
 
-def _pool_by_superpoint(feats_rows, spp_rows):
+def _pool_by_superpoint(feats_rows, spp_rows, return_inverse=False):
     """scatter-mean of `feats_rows` over unique(spp_rows) in sorted-id order, index-ordered float32 sums
     (gapro_densify_spp + gapro_pool_feats): what gaussian_process_utils.py:66-70 does with torch_scatter."""
     lib = _lib.load()
@@ -128,7 +128,17 @@ def _pool_by_superpoint(feats_rows, spp_rows):
     src = feats_rows.float().contiguous()
     _lib.check(lib.gapro_pool_feats(src.data_ptr(), perm.data_ptr(), seg.data_ptr(), S, D, out.data_ptr(), stream),
                "gapro_pool_feats")
-    return out
+    return (out, gid.long()) if return_inverse else out
+
+
+def _nearest_rows(coords_rows, centroid, npoint_nearest):
+    """rows kept by the top-k-nearest rule (gaussian_process_utils.py:73-83): all of them up to
+    `npoint_nearest`, else the `npoint_nearest` closest to `centroid`, nearest first."""
+    n = int(coords_rows.shape[0])
+    if n <= npoint_nearest:
+        return torch.arange(n, device=coords_rows.device)
+    d = ((coords_rows - centroid[None, :]) ** 2).sum(1)
+    return torch.topk(d, k=npoint_nearest, largest=False)[1]
 
 
 def fit_gp(coords_float, feats, spp, b1_inds, b2_inds, intersect_inds, training_iter=50, npoint_nearest=800,
@@ -147,12 +157,8 @@ def fit_gp(coords_float, feats, spp, b1_inds, b2_inds, intersect_inds, training_
         b2_feats = _pool_by_superpoint(b2_feats, spp[b2_inds])
     else:
         centroid = coords_float[intersect_inds].mean(0)
-        if len(b1_inds) > npoint_nearest:
-            d = ((coords_float[b1_inds] - centroid[None, :]) ** 2).sum(1)
-            b1_feats = b1_feats[torch.topk(d, k=npoint_nearest, largest=False)[1]]
-        if len(b2_inds) > npoint_nearest:
-            d = ((coords_float[b2_inds] - centroid[None, :]) ** 2).sum(1)
-            b2_feats = b2_feats[torch.topk(d, k=npoint_nearest, largest=False)[1]]
+        b1_feats = b1_feats[_nearest_rows(coords_float[b1_inds], centroid, npoint_nearest)]
+        b2_feats = b2_feats[_nearest_rows(coords_float[b2_inds], centroid, npoint_nearest)]
     n1, n2 = int(b1_feats.shape[0]), int(b2_feats.shape[0])
     test = feats[intersect_inds]
     table = torch.cat([b1_feats, b2_feats, test], 0).contiguous()
@@ -160,3 +166,42 @@ def fit_gp(coords_float, feats, spp, b1_inds, b2_inds, intersect_inds, training_
                          init_noise=None if init_noise is None else [init_noise], training_iter=training_iter)[0]
     probs, conf, labels = res[0], res[1], res[2]
     return probs, conf, labels, probs * (1 - probs)
+
+
+def fit_gp_ensemble(coords_float, feats, spp, b1_inds, b2_inds, intersect_inds, channel_dims, training_iter=50,
+                    npoint_nearest=800, spp_pool=True, *, init_noise=None):
+    """Drop-in for fit_gp_ensemble (/root/reference/gapro/gaussian_process_utils.py:119-251): one GP per
+    channel group feats[:, channel_dims[i]:channel_dims[i+1]], all on the same rows (top-k-nearest points
+    of each box, then superpoint means when spp_pool; the intersection is pooled too and the result
+    broadcast back to its points, :243-249).  The two score columns are accumulated exactly as there
+    (:236-237: column 1 receives max(p, 1-p) and column 0 min(p, 1-p) of every member, so the returned label
+    is 1 unless the columns tie) - the mirror keeps that behaviour.  Returns (pred_probs, pred_labels,
+    pred_variance) with pred_variance the summed Bernoulli variances.  `init_noise`: one array per group."""
+    if not feats.is_cuda:
+        raise _lib.GaproError("fit_gp_ensemble needs CUDA tensors; gapro_b200 has no CPU fallback")
+    feats = feats.float()
+    centroid = coords_float[intersect_inds].mean(0)
+    k1 = _nearest_rows(coords_float[b1_inds], centroid, npoint_nearest)
+    k2 = _nearest_rows(coords_float[b2_inds], centroid, npoint_nearest)
+    b1_feats, b2_feats, test = feats[b1_inds][k1], feats[b2_inds][k2], feats[intersect_inds]
+    inverse = None
+    if spp_pool:
+        b1_feats = _pool_by_superpoint(b1_feats, spp[b1_inds][k1])
+        b2_feats = _pool_by_superpoint(b2_feats, spp[b2_inds][k2])
+        test, inverse = _pool_by_superpoint(test, spp[intersect_inds], return_inverse=True)
+    n1, n2, nt = int(b1_feats.shape[0]), int(b2_feats.shape[0]), int(test.shape[0])
+    table = torch.cat([b1_feats, b2_feats, test], 0)
+    score = torch.zeros((nt, 2), dtype=torch.float32, device=feats.device)
+    variance = torch.zeros(nt, dtype=torch.float32, device=feats.device)
+    for g in range(len(channel_dims) - 1):
+        sub = table[:, channel_dims[g]:channel_dims[g + 1]].contiguous()
+        probs, conf = fit_gp_regions(sub, [np.arange(n1 + n2)], [n1], [np.arange(n1 + n2, n1 + n2 + nt)],
+                                     init_noise=None if init_noise is None else [init_noise[g]],
+                                     training_iter=training_iter)[0][:2]
+        score[:, 1] += conf
+        score[:, 0] += 1 - conf
+        variance += probs * (1 - probs)
+    pred_probs, pred_labels = torch.max(score, dim=1)
+    if inverse is not None:
+        pred_probs, pred_labels, variance = pred_probs[inverse], pred_labels[inverse], variance[inverse]
+    return pred_probs, pred_labels, variance

@@ -318,3 +318,48 @@ def fit_gp_points_oracle(coords_float, feats, spp, b1_inds, b2_inds, intersect_i
     r = fit_region_autograd(np.concatenate([f1, f2]), len(f1), feats[intersect_inds], init_noise, iters=training_iter)
     p = r["prob"]
     return p, r["conf"], r["label"], (p * (np.float32(1.0) - p)).astype(np.float32)
+
+
+def fit_gp_ensemble_oracle(coords_float, feats, spp, b1_inds, b2_inds, intersect_inds, channel_dims, init_noise,
+                           training_iter=50, npoint_nearest=800, spp_pool=True):
+    """Restates fit_gp_ensemble (/root/reference/gapro/gaussian_process_utils.py:119-251), fp64 policy per member.
+    Returns (probs, labels, variance) per intersection point."""
+    from .gen_ps_oracle import scatter_sum_index_order
+    coords = np.asarray(coords_float, dtype=np.float64)
+    feats = np.asarray(feats, dtype=np.float32)
+    spp = np.asarray(spp)
+    c = coords[intersect_inds].mean(0)
+
+    def nearest(idx):
+        if len(idx) <= npoint_nearest:
+            return idx
+        d = ((coords[idx] - c[None, :]) ** 2).sum(1)
+        return idx[np.argsort(d, kind="stable")[:npoint_nearest]]
+
+    def pooled(idx):
+        _, dense = np.unique(spp[idx], return_inverse=True)
+        dense = dense.reshape(-1)
+        s, cnt = scatter_sum_index_order(feats[idx], dense, int(dense.max()) + 1)
+        return s / np.maximum(cnt, 1).astype(np.float32)[:, None], dense
+
+    i1, i2 = nearest(np.asarray(b1_inds)), nearest(np.asarray(b2_inds))
+    if spp_pool:
+        f1, f2 = pooled(i1)[0], pooled(i2)[0]
+        ft, inverse = pooled(np.asarray(intersect_inds))
+    else:
+        f1, f2, ft, inverse = feats[i1], feats[i2], feats[intersect_inds], None
+    score = np.zeros((len(ft), 2), dtype=np.float32)
+    variance = np.zeros(len(ft), dtype=np.float32)
+    for g in range(len(channel_dims) - 1):
+        a, b = channel_dims[g], channel_dims[g + 1]
+        r = fit_region_autograd(np.concatenate([f1[:, a:b], f2[:, a:b]]), len(f1), ft[:, a:b], init_noise[g],
+                                iters=training_iter)
+        p, lab = r["prob"], r["label"]
+        score[:, 1] += np.where(lab, p, np.float32(1) - p)
+        score[:, 0] += np.where(lab, np.float32(1) - p, p)
+        variance += p * (np.float32(1) - p)
+    labels = score.argmax(1)
+    probs = score.max(1)
+    if inverse is not None:
+        probs, labels, variance = probs[inverse], labels[inverse], variance[inverse]
+    return probs, labels, variance

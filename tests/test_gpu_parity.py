@@ -259,6 +259,36 @@ def test_point_level_fit_gp_variant(dev, lib, spp_pool):
     assert (got[2].cpu().numpy()[sure] == ref[2][sure]).all()
 
 
+@pytest.mark.parametrize("spp_pool", [True, False])
+def test_channel_group_ensemble_variant(dev, lib, spp_pool):
+    """fit_gp_ensemble (gaussian_process_utils.py:119-251), two channel groups."""
+    from gapro_b200.gaussian_process_utils import fit_gp_ensemble
+    from oracle import gp_oracle as G
+    inp = synthetic_inputs(synthetic.make_scene(12, "tiny"))
+    rng = np.random.default_rng(9)
+    N = len(inp["xyz"])
+    order = rng.permutation(N)
+    b1, b2, inter = np.sort(order[:700]), np.sort(order[700:1100]), np.sort(order[1100:1160])
+    feats = inp["mask_feats"].astype(np.float32)
+    dims = [0, 3, feats.shape[1]]
+    kw = dict(npoint_nearest=120, spp_pool=spp_pool)
+    nz = [rng.standard_normal(240).astype(np.float32) for _ in range(2)]  # upper bound on training rows
+    T = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+    if spp_pool:
+        # the number of training rows (superpoints among the 120 nearest points of each box) comes from the data
+        c = inp["xyz"][inter].astype(np.float64).mean(0)
+        near = lambda idx: idx[np.argsort(((inp["xyz"][idx].astype(np.float64) - c) ** 2).sum(1), kind="stable")[:120]]
+        m = len(np.unique(inp["spp"][near(b1)])) + len(np.unique(inp["spp"][near(b2)]))
+        nz = [z[:m] for z in nz]
+    ref = G.fit_gp_ensemble_oracle(inp["xyz"], feats, inp["spp"], b1, b2, inter, dims, nz, **kw)
+    got = fit_gp_ensemble(T(inp["xyz"], torch.float64), T(feats, torch.float32), T(inp["spp"], torch.int64),
+                          T(b1, torch.int64), T(b2, torch.int64), T(inter, torch.int64), dims, init_noise=nz, **kw)
+    assert len(got) == 3 and all(len(t) == len(inter) for t in got)
+    assert np.allclose(got[0].cpu().numpy(), ref[0], rtol=1e-4, atol=1e-7)
+    assert np.allclose(got[2].cpu().numpy(), ref[2], rtol=1e-4, atol=1e-7)
+    assert (got[1].cpu().numpy() == ref[1]).all()
+
+
 def test_gp_degenerate_regions(dev, lib):
     from gapro_b200.gaussian_process_utils import fit_gp_regions, fit_gp_spp
     from oracle import gp_oracle as G
