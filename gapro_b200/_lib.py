@@ -26,8 +26,10 @@ _SIGNATURES = {
     "gapro_floor_boxes": (ctypes.c_int, [P, P, P, c_int32, c_int64, c_double, P, P, P, P]),
     "gapro_occupancy": (ctypes.c_int, [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_double, c_float,
                                        P, P, P, P, P, P]),
-    "gapro_heuristic_labels": (ctypes.c_int, [P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
-                                              P, P, P]),
+    "gapro_heuristic_labels": (ctypes.c_int, [P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                              c_float, P, P, P]),
+    "gapro_multibox_workspace_bytes": (c_size_t, [c_int64]),
+    "gapro_multibox_sources": (ctypes.c_int, [P, P, P, P, c_int32, c_int64, P, P, c_size_t, P]),
     "gapro_pool_feats": (ctypes.c_int, [P, P, P, c_int32, c_int32, P, P]),
     "gapro_enumerate_events": (ctypes.c_int, [P, c_int32, P, P, c_int32, P, P, P, c_int32]),
     "gapro_box_iou": (ctypes.c_int, [P, c_int32, P]),

@@ -490,6 +490,94 @@ extern "C" int gapro_occupancy(const double* xyz, const int32_t* perm, const int
 }
 
 // =============================================================================================
+// Source point of the "dist" rule.  gen_pseudo_label computes, for the points that lie in several
+// boxes, point_inds = nonzero(bb_occupancy[num_BBs_per_point > 1])[0] (gen_ps_utils.py:516) - row
+// numbers of the COMPACTED sub-matrix - and then reads coords_float[point_inds] (:526): the k-th
+// multi-box point of a scene is measured from the coordinates of point k of that scene.  To return what
+// the reference returns, dist_src[p] = scene base + (number of multi-box points before p in the scene)
+// for multi-box points, p otherwise: per-point flag, exclusive scan, subtract the scan at the scene base.
+// =============================================================================================
+__device__ __forceinline__ int find_scene_pt(const int64_t* __restrict__ pt_off, int n_scenes, int64_t p) {
+    int lo = 0, hi = n_scenes;            // pt_off[lo] <= p < pt_off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pt_off[mid] <= p) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+k_multibox_flag(const double* __restrict__ xyz, const int64_t* __restrict__ pt_off, const int32_t* __restrict__ box_off,
+                const float* __restrict__ boxes, int n_scenes, int64_t n, int32_t* __restrict__ flag) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int sc = find_scene_pt(pt_off, n_scenes, p);
+    const double x = xyz[3 * p], y = xyz[3 * p + 1], z = xyz[3 * p + 2];
+    const float MARGIN = 0.005f;
+    int n_in = 0;
+    for (int b = box_off[sc]; b < box_off[sc + 1]; ++b) {
+        const float* bx = boxes + 6 * (size_t)b;
+        n_in += x >= (double)__fsub_rn(bx[0], MARGIN) && y >= (double)__fsub_rn(bx[1], MARGIN) &&
+                z >= (double)__fsub_rn(bx[2], MARGIN) && x <= (double)__fadd_rn(bx[3], MARGIN) &&
+                y <= (double)__fadd_rn(bx[4], MARGIN) && z <= (double)__fadd_rn(bx[5], MARGIN);
+    }
+    flag[p] = n_in > 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_multibox_src(const int32_t* __restrict__ flag, const int32_t* __restrict__ scan, const int64_t* __restrict__ pt_off,
+               int n_scenes, int64_t n, int32_t* __restrict__ dist_src) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int64_t base = pt_off[find_scene_pt(pt_off, n_scenes, p)];
+    dist_src[p] = flag[p] ? (int32_t)(base + (scan[p] - scan[base])) : (int32_t)p;
+}
+
+struct MultiboxWs {
+    size_t flag, scan, cub_tmp, cub_bytes, total;
+};
+static MultiboxWs multibox_layout(int64_t n) {
+    MultiboxWs w;
+    w.flag = 0;
+    w.scan = gapro_align_up((size_t)n * 4, 256);
+    w.cub_tmp = w.scan + gapro_align_up((size_t)n * 4, 256);
+    w.cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, w.cub_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+    w.total = w.cub_tmp + gapro_align_up(w.cub_bytes, 256);
+    return w;
+}
+
+extern "C" size_t gapro_multibox_workspace_bytes(int64_t n_points) {
+    if (n_points <= 0) return 0;
+    return multibox_layout(n_points).total;
+}
+
+extern "C" int gapro_multibox_sources(const double* xyz, const int64_t* pt_off_dev, const int32_t* box_off_dev,
+                                      const float* boxes, int32_t n_scenes, int64_t n_points, int32_t* dist_src,
+                                      void* ws, size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GAPRO_REQUIRE(xyz && pt_off_dev && box_off_dev && boxes && dist_src && ws, "gapro_multibox_sources: null pointer");
+    GAPRO_REQUIRE(n_scenes > 0 && n_points > 0 && n_points < (int64_t)INT32_MAX, "gapro_multibox_sources: empty batch");
+    const MultiboxWs w = multibox_layout(n_points);
+    if (ws_bytes < w.total) {
+        gapro_set_error("gapro_multibox_sources: workspace %zu < %zu bytes", ws_bytes, w.total);
+        return GAPRO_ERR_WORKSPACE;
+    }
+    char* base = (char*)ws;
+    int32_t* flag = (int32_t*)(base + w.flag);
+    int32_t* scan = (int32_t*)(base + w.scan);
+    const int T = 256;
+    const unsigned G = (unsigned)((n_points + T - 1) / T);
+    k_multibox_flag<<<G, T, 0, stream>>>(xyz, pt_off_dev, box_off_dev, boxes, n_scenes, n_points, flag);
+    GAPRO_KERNEL_CHECK();
+    size_t tmp = w.cub_bytes;
+    GAPRO_CUDA_TRY(cub::DeviceScan::ExclusiveSum(base + w.cub_tmp, tmp, flag, scan, (int)n_points, stream));
+    k_multibox_src<<<G, T, 0, stream>>>(flag, scan, pt_off_dev, n_scenes, n_points, dist_src);
+    GAPRO_KERNEL_CHECK();
+    return GAPRO_OK;
+}
+
+// =============================================================================================
 // Heuristic labelers: gen_pseudo_label_box2mask (gen_ps_utils.py:242-290) and
 // gen_pseudo_label (:485-569) + spp_align_label (:99-129).  Per-POINT containment in the instance
 // boxes (margins evaluated in float32, the dtype of instance_box there), per-point rule for points
@@ -502,8 +590,8 @@ template <int WORDS>
 __global__ void __launch_bounds__(256)
 k_heuristic(const double* __restrict__ xyz, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
             const int32_t* __restrict__ spp_off, const int32_t* __restrict__ box_off, const float* __restrict__ boxes,
-            const float* __restrict__ vol, int n_scenes, int s_total, int rule, int spp_align, float occ_thresh,
-            int32_t* __restrict__ inst_spp, int32_t* __restrict__ inst_pt) {
+            const float* __restrict__ vol, const int32_t* __restrict__ dist_src, int n_scenes, int s_total, int rule,
+            int spp_align, float occ_thresh, int32_t* __restrict__ inst_spp, int32_t* __restrict__ inst_pt) {
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= s_total) return;
@@ -586,6 +674,15 @@ k_heuristic(const double* __restrict__ xyz, const int32_t* __restrict__ perm, co
         } else if (n_in > 1 && rule != 2) {
             double best = 0.0;
             int arg = -1;
+            double qx = x, qy = y, qz = z;
+            if (rule == 1) {
+                // gen_ps_utils.py:526 measures the k-th multi-box point of the scene from the coordinates of
+                // point k (it indexes coords_float with row numbers of the compacted sub-matrix): dist_src
+                const int64_t q = dist_src[p];
+                qx = xyz[3 * q];
+                qy = xyz[3 * q + 1];
+                qz = xyz[3 * q + 2];
+            }
 #pragma unroll
             for (int w = 0; w < WORDS; ++w) {
                 uint32_t m = mask[w];
@@ -600,7 +697,7 @@ k_heuristic(const double* __restrict__ xyz, const int32_t* __restrict__ perm, co
                         const double cx = (double)__fdiv_rn(__fadd_rn(bx[0], bx[3]), 2.0f);
                         const double cy = (double)__fdiv_rn(__fadd_rn(bx[1], bx[4]), 2.0f);
                         const double cz = (double)__fdiv_rn(__fadd_rn(bx[2], bx[5]), 2.0f);
-                        const double dx = __dsub_rn(x, cx), dy = __dsub_rn(y, cy), dz = __dsub_rn(z, cz);
+                        const double dx = __dsub_rn(qx, cx), dy = __dsub_rn(qy, cy), dz = __dsub_rn(qz, cz);
                         key = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                     }
                     if (arg < 0 || key < best) {
@@ -647,21 +744,23 @@ k_heuristic(const double* __restrict__ xyz, const int32_t* __restrict__ perm, co
 
 extern "C" int gapro_heuristic_labels(const double* xyz, const int32_t* perm, const int32_t* seg_off,
                                       const int32_t* spp_off_dev, const int32_t* box_off_dev, const float* boxes,
-                                      const float* boxes_vol, int32_t n_scenes, int32_t s_total, int32_t words,
-                                      int32_t rule, int32_t spp_align, float occ_thresh, int32_t* inst_spp,
-                                      int32_t* inst_pt, void* stream_) {
+                                      const float* boxes_vol, const int32_t* dist_src, int32_t n_scenes,
+                                      int32_t s_total, int32_t words, int32_t rule, int32_t spp_align, float occ_thresh,
+                                      int32_t* inst_spp, int32_t* inst_pt, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GAPRO_REQUIRE(xyz && perm && seg_off && spp_off_dev && box_off_dev && boxes && boxes_vol, "gapro_heuristic_labels: null pointer");
     GAPRO_REQUIRE(spp_align ? inst_spp != nullptr : inst_pt != nullptr, "gapro_heuristic_labels: missing output array");
     GAPRO_REQUIRE(rule >= 0 && rule <= 2, "gapro_heuristic_labels: rule must be 0 (volume), 1 (dist) or 2 (none)");
+    GAPRO_REQUIRE(rule != 1 || dist_src != nullptr,
+                  "gapro_heuristic_labels: rule 1 (dist) needs dist_src from gapro_multibox_sources");
     GAPRO_REQUIRE(n_scenes > 0 && s_total > 0, "gapro_heuristic_labels: empty batch");
     GAPRO_REQUIRE(words == 1 || words == 2 || words == 4 || words == 8,
                   "gapro_heuristic_labels: words must be 1, 2, 4 or 8 (at most 256 boxes per scene)");
     const int T = 256, WPB = T / 32;
     unsigned G = (unsigned)((s_total + WPB - 1) / WPB);
 #define LAUNCH_H(W)                                                                                                 \
-    k_heuristic<W><<<G, T, 0, stream>>>(xyz, perm, seg_off, spp_off_dev, box_off_dev, boxes, boxes_vol, n_scenes,   \
-                                        s_total, rule, spp_align, occ_thresh, inst_spp, inst_pt)
+    k_heuristic<W><<<G, T, 0, stream>>>(xyz, perm, seg_off, spp_off_dev, box_off_dev, boxes, boxes_vol, dist_src,   \
+                                        n_scenes, s_total, rule, spp_align, occ_thresh, inst_spp, inst_pt)
     switch (words) {
         case 1: LAUNCH_H(1); break;
         case 2: LAUNCH_H(2); break;

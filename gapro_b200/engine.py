@@ -353,8 +353,18 @@ class GaproEngine:
         inst_spp = torch.empty(St, dtype=torch.int32, device=dev)
         inst_pt = torch.empty(N, dtype=torch.int32, device=dev)
         thr = -1.0 if occ_thresh is None else float(np.float32(occ_thresh))
+        dist_src = None
+        if rule_id == 1:
+            # the reference measures the k-th multi-box point from the coordinates of point k (gen_ps_utils.py:516,526)
+            dist_src = torch.empty(N, dtype=torch.int32, device=dev)
+            mws = self._workspace("multibox", lib.gapro_multibox_workspace_bytes(N))
+            pt_off_dev = self._dev(pt_off)
+            _lib.check(lib.gapro_multibox_sources(xyz.data_ptr(), pt_off_dev.data_ptr(), box_off_dev.data_ptr(),
+                                                  boxes.data_ptr(), 1, N, dist_src.data_ptr(), mws.data_ptr(),
+                                                  mws.numel(), stream), "gapro_multibox_sources")
         _lib.check(lib.gapro_heuristic_labels(xyz.data_ptr(), perm.data_ptr(), seg_off.data_ptr(), spp_off_dev.data_ptr(),
-                                              box_off_dev.data_ptr(), boxes.data_ptr(), vol.data_ptr(), 1, St, words,
+                                              box_off_dev.data_ptr(), boxes.data_ptr(), vol.data_ptr(),
+                                              0 if dist_src is None else dist_src.data_ptr(), 1, St, words,
                                               rule_id, 1 if spp_align else 0, thr, inst_spp.data_ptr(),
                                               inst_pt.data_ptr(), stream), "gapro_heuristic_labels")
         if spp_align:

@@ -42,7 +42,7 @@ def get_miou_scene(semantic_label, instance_label, ps_semantic_label, ps_instanc
     area_g = table[1:, :].sum(1).float()
     area_p = table[:, 1:].sum(0).float()
     union = area_g[:, None] + area_p[None, :] - inter
-    ious = inter / (union + 1e-6)
+    ious = inter / (union + 1e-4)                     # cal_iou, eval_ps_labels.py:40
     ious = ious * (gt_cls[:, None] == ps_cls[None, :]).float()
     max_ious = ious.max(dim=1)[0]
     return max_ious[gt_cls >= 0]

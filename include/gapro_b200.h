@@ -128,15 +128,29 @@ int gapro_occupancy(const double* xyz, const int32_t* perm, const int32_t* seg_o
  *   boxes      dev float[n_boxes,6], boxes_vol dev float[n_boxes]  (instance boxes only; box_off_dev
  *              indexes them per scene)
  *   rule       0 = smallest volume, 1 = nearest box centre, 2 = none (such points vote background)
+ *   dist_src   dev int32[n], required for rule 1, NULL otherwise: the point whose coordinates the distance
+ *              to the box centres is measured from (gapro_multibox_sources below)
  *   spp_align  1: majority vote per superpoint -> inst_spp[S_total] (box index or -1);
  *              0: per-point result -> inst_pt[n] (box index, -1 background, -2 undecided)
  *   occ_thresh >= 0: only boxes holding >= occ_thresh of the superpoint may win the vote (0.7 in
  *              gen_pseudo_label); < 0: no restriction (gen_pseudo_label_box2mask)
  */
 int gapro_heuristic_labels(const double* xyz, const int32_t* perm, const int32_t* seg_off, const int32_t* spp_off_dev,
-                           const int32_t* box_off_dev, const float* boxes, const float* boxes_vol, int32_t n_scenes,
-                           int32_t s_total, int32_t words, int32_t rule, int32_t spp_align, float occ_thresh,
-                           int32_t* inst_spp, int32_t* inst_pt, void* stream);
+                           const int32_t* box_off_dev, const float* boxes, const float* boxes_vol,
+                           const int32_t* dist_src, int32_t n_scenes, int32_t s_total, int32_t words, int32_t rule,
+                           int32_t spp_align, float occ_thresh, int32_t* inst_spp, int32_t* inst_pt, void* stream);
+
+/* Source points of the "dist" rule.  gen_ps_utils.py:516 takes point_inds from nonzero() of the COMPACTED
+ * matrix bb_occupancy[num_BBs_per_point > 1] and :526 indexes coords_float with them, so the k-th multi-box
+ * point of a scene is measured from the coordinates of point k of that scene.  dist_src[p] = scene base + k
+ * for the k-th multi-box point, p for every other point (found by executing the reference, see
+ * tests/golden/make_ref_golden.py).
+ *   pt_off_dev dev int64[n_scenes+1]; ws >= gapro_multibox_workspace_bytes(n_points)
+ */
+size_t gapro_multibox_workspace_bytes(int64_t n_points);
+int gapro_multibox_sources(const double* xyz, const int64_t* pt_off_dev, const int32_t* box_off_dev,
+                           const float* boxes, int32_t n_scenes, int64_t n_points, int32_t* dist_src, void* ws,
+                           size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
  * B — superpoint feature pooling.  Replaces

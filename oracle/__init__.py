@@ -5,14 +5,19 @@ package; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs do, and there only as the checker
 or the timed CPU baseline — never as the product path.
 
-PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or
-fixtures for this path and its arithmetic lives in two
-un-vendored third-party dependencies that are not installable here
-(``gpytorch`` — version not pinned by the reference, restated at 1.8.1-style
-constants — and ``torch_scatter==2.0.9``).  The oracle is therefore a
-restatement of `/root/reference/gapro/gen_ps_utils.py`,
-`/root/reference/gapro/gaussian_process_utils.py` and of those libraries'
-published algorithms, validated only against itself (autograd vs. hand-derived
-gradients, torch ops vs. explicit loops) and against hand-built known-answer
-cases in ``tests/``.
+PINNING.  The scene-level restatement (`gen_ps_oracle.py`, `heuristic_oracle.py`)
+is pinned to the reference's own code: `tests/golden/make_ref_golden.py` imports
+`/root/reference/gapro/gen_ps_utils.py` and `eval_ps_labels.py` as they lie,
+executes them on CPU (stand-ins only for the two absent dependencies: a
+sequential `torch_scatter` shim and `fit_gp_spp` -> this oracle's GP fit) and
+commits their outputs as `tests/golden/ref_outputs.npz`;
+`tests/test_reference_run.py` requires the oracle to reproduce them bit for bit.
+
+PARITY UNPINNED for the inside of the GP fit (`gp_oracle.py`): its arithmetic
+lives in `gpytorch` (version not pinned by the reference, restated at
+1.8.1-style constants), which is not installable here, and the reference ships
+no golden vectors for it.  That part is a restatement of
+`/root/reference/gapro/gaussian_process_utils.py` and of gpytorch's published
+algorithm, validated only against itself (autograd vs. hand-derived gradients,
+torch ops vs. explicit loops).
 """

@@ -56,9 +56,12 @@ def heuristic_labels(coords_float, spp, instance_cls, instance_box, instance_box
             inst[i] = bs[np.argmin(vol[bs])]
     elif heuristic_rule == "dist":
         centre = ((box[:, :3] + box[:, 3:]) / np.float32(2.0)).astype(np.float64)
-        for i in multi:
+        # gen_ps_utils.py:526 indexes coords_float with `point_inds`, which are row numbers of the COMPACTED
+        # sub-matrix bb_occupancy[num_BBs_per_point > 1] (:516), not point ids: the k-th multi-box point is
+        # measured from the coordinates of point k.  Restated as it executes.
+        for rank, i in enumerate(multi):
             bs = np.flatnonzero(occ[i])
-            d = coords[i][None, :] - centre[bs]
+            d = coords[rank][None, :] - centre[bs]
             d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
             inst[i] = bs[np.argmin(d2)]
     elif heuristic_rule == "none":

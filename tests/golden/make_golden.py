@@ -1,8 +1,8 @@
 """Regenerates the committed golden vectors.  The reference itself cannot be imported here
 (gpytorch / torch_scatter are absent), so these vectors are OUTPUTS OF THE ORACLE
 (fp64 policy) — they pin the oracle against accidental drift and let the GPU box check the CUDA
-path without re-running the slow oracle; they do NOT pin the oracle to the reference ("parity
-unpinned", see oracle/__init__.py).
+path without re-running the slow oracle; they do NOT pin the oracle to the reference (that is
+make_ref_golden.py's job for the scene pipeline; the GP fit stays "parity unpinned", see oracle/__init__.py).
 
     python tests/golden/make_golden.py
 """

@@ -105,7 +105,7 @@ def test_miou_scene_against_brute_force():
             mj = ps_inst == j
             if not mj.any() or ps_sem[torch.nonzero(mj)[0, 0]] != ci:
                 continue
-            best = max(best, float((mi & mj).sum()) / (float((mi | mj).sum()) + 1e-6))
+            best = max(best, float((mi & mj).sum()) / (float((mi | mj).sum()) + 1e-4))
         exp.append(best)
     assert np.allclose(got.numpy(), np.array(exp), atol=1e-6)
     conf = eval_ps_labels.get_scene_sem_conf(sem, ps_sem.clone(), num_classes=19)
