@@ -25,12 +25,12 @@ def _plane_normal(q):
     A = np.column_stack([q[:, 0], q[:, 1], np.ones(4)])
     AtA = A.T @ A
     if np.linalg.det(AtA) > 1e-10:
-        fit = np.linalg.inv(AtA) @ (A.T @ q[:, 2])
+        fit = (np.linalg.inv(AtA) @ A.T) @ q[:, 2]               # (A^T A)^-1 A^T first, then z: the reference's product order
         with np.errstate(divide="ignore", invalid="ignore"):     # plane through the origin: NaN, as in the reference
             n = np.array([fit[0] / fit[2], fit[1] / fit[2], -1.0 / fit[2]])
     else:
         A2 = A[:, :2]
-        fit = np.linalg.inv(A2.T @ A2) @ (A2.T @ -np.ones(4))
+        fit = (np.linalg.inv(A2.T @ A2) @ A2.T) @ -np.ones(4)
         n = np.array([fit[0], fit[1], 0.0])
     with np.errstate(invalid="ignore"):
         return n / np.linalg.norm(n)

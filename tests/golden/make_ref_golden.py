@@ -238,6 +238,42 @@ def main():
     finally:
         torch.Tensor.cuda = cuda
     out["conf_gt"], out["conf_ps"], out["conf_matrix"] = gt.numpy(), ps.numpy(), np.asarray(conf)
+    # --- wall boxes from a ScanNet-planes file (scannet_planes.py:177-230); np.int was removed from numpy, restore the alias
+    import json
+    import tempfile
+    import scannet_planes as P
+    if not hasattr(np, "int"):
+        np.int = int
+    rng = np.random.default_rng(21)
+    # a slightly rotated room in the raw (y-up) convention, 4 walls + floor + ceiling + a slanted roof quad,
+    # a non-planar quad and a triangle
+    c, s_ = np.cos(0.3), np.sin(0.3)
+    base = np.array([[0, 0], [5.2, 0], [5.2, 3.9], [0, 3.9]]) @ np.array([[c, -s_], [s_, c]]).T + [1.0, -2.0]
+    verts = [[float(x), 0.0, float(-y)] for x, y in base] + [[float(x), 2.7, float(-y)] for x, y in base]
+    verts += [[2.0, 2.7, 1.0], [3.0, 3.4, 1.0], [3.0, 3.4, 2.5], [2.0, 2.7, 2.5]]          # slanted
+    verts += [[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [1.0, 1.0, 0.7], [0.0, 1.0, -0.9]]          # not coplanar
+    verts = (np.array(verts) + rng.normal(0, 1e-3, (len(verts), 3))).tolist()
+    quads = [[0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [3, 0, 4, 7], [0, 1, 2, 3], [4, 5, 6, 7],
+             [8, 9, 10, 11], [12, 13, 14, 15], [0, 1, 2]]
+    plane_text = json.dumps({"verts": verts, "quads": quads})
+    A = np.array([[0.94, 0.34, 0, -1.5], [-0.34, 0.94, 0, 2.25], [0, 0, 1, -0.05], [0, 0, 0, 1]])
+    align_text = "axisAlignment = " + " ".join(repr(float(v)) for v in A.reshape(-1)) + "\nnumDepthFrames = 1\n"
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "dataset/scannetv2/scannet_planes"))
+        os.makedirs(os.path.join(tmp, "dataset/scannetv2/scans_transform/scene0000_00"))
+        open(os.path.join(tmp, "dataset/scannetv2/scannet_planes/scene0000_00.json"), "w").write(plane_text)
+        open(os.path.join(tmp, "dataset/scannetv2/scans_transform/scene0000_00/scene0000_00.txt"), "w").write(align_text)
+        os.chdir(tmp)
+        try:
+            wcls, wbox, wvol = P.get_wall_boxes("scene0000_00")
+            missing = P.get_wall_boxes("scene0000_01")
+        finally:
+            os.chdir(cwd)
+    assert missing == ([], [], [])
+    out["planes_json"], out["planes_align"] = np.array(plane_text), np.array(align_text)
+    out["planes_cls"], out["planes_box"], out["planes_vol"] = np.asarray(wcls), np.asarray(wbox), np.asarray(wvol)
+    print(f"wall boxes: {len(wbox)} of {len(quads)} quads kept")
     np.savez_compressed(os.path.join(HERE, "ref_outputs.npz"), **out)
     print("wrote", os.path.join(HERE, "ref_outputs.npz"))
 

@@ -120,6 +120,20 @@ def test_confusion_matrix_equals_reference_run(ref):
     assert np.array_equal(conf.numpy(), ref["conf_matrix"])
 
 
+def test_wall_boxes_equal_reference_run(ref, tmp_path):
+    """scannet_planes.get_wall_boxes on the files the reference was run on (planes json + axis alignment)."""
+    from gapro_b200 import scannet_planes
+    (tmp_path / "planes").mkdir()
+    (tmp_path / "tf" / "scene0000_00").mkdir(parents=True)
+    (tmp_path / "planes" / "scene0000_00.json").write_text(str(ref["planes_json"]))
+    (tmp_path / "tf" / "scene0000_00" / "scene0000_00.txt").write_text(str(ref["planes_align"]))
+    cls, box, vol = scannet_planes.get_wall_boxes("scene0000_00", planes_root=str(tmp_path / "planes"),
+                                                  transform_root=str(tmp_path / "tf"))
+    assert len(ref["planes_box"]) >= 4
+    assert np.array_equal(np.asarray(cls), ref["planes_cls"])
+    assert np.array_equal(np.asarray(box), ref["planes_box"]) and np.array_equal(np.asarray(vol), ref["planes_vol"])
+
+
 # ------------------------------------------------------------------------------------------------
 # CUDA path against the reference run
 # ------------------------------------------------------------------------------------------------
