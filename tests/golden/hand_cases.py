@@ -52,3 +52,43 @@ def hand_cases():
     out["with_wall"] = _case(np.concatenate([grid_points(a[:3], a[3:], 6), grid_points(b[:3], b[3:], 6)]), [a, b],
                              cls=[2, 9], walls=wall, seed=7)
     return out
+
+
+CLI_SCANS = ["scene0000_00", "scene0001_00", "scene0002_01"]
+CLI_SEED = 7
+
+
+def cli_noise_seed(scan, seed=CLI_SEED):
+    """noise seed the product CLI derives for a scan from --seed (gapro_b200/gen_ps.py)."""
+    import zlib
+    return (zlib.crc32(scan.encode()) ^ seed) & 0x7FFFFFFF
+
+
+def write_cli_dataset(root):
+    """dataset/scannetv2 as gen_ps.py:27-58 expects it under `root` (a pathlib.Path): three tiny synthetic scans,
+    a planes json for the first one.  Returns {scan: Scene}."""
+    import json
+
+    import torch
+
+    from gapro_b200 import synthetic
+    ds = root / "dataset" / "scannetv2"
+    for sub in ("train", "superpoints", "scans_transform", "scannet_planes"):
+        (ds / sub).mkdir(parents=True, exist_ok=True)
+    scenes = {}
+    for i, scan in enumerate(CLI_SCANS):
+        sc = synthetic.make_scene(40 + i, "tiny")
+        scenes[scan] = sc
+        torch.save((sc.xyz_raw, sc.rgb, sc.sem, sc.inst), str(ds / "train" / f"{scan}_inst_nostuff.pth"))
+        torch.save(sc.spp, str(ds / "superpoints" / f"{scan}.pth"))
+        (ds / "scans_transform" / scan).mkdir(exist_ok=True)
+        (ds / "scans_transform" / scan / f"{scan}.txt").write_text(
+            "axisAlignment = " + " ".join(repr(float(x)) for x in sc.axis_align.ravel()) + "\nnumColorFrames = 1\n")
+    # planes file of the first scan: the four walls of its bounding rectangle in the RAW (y-up) frame of the file
+    sc = scenes[CLI_SCANS[0]]
+    lo, hi = sc.xyz_raw.min(0), sc.xyz_raw.max(0)
+    base = [[lo[0], lo[1]], [hi[0], lo[1]], [hi[0], hi[1]], [lo[0], hi[1]]]
+    verts = [[float(x), float(lo[2]), float(-y)] for x, y in base] + [[float(x), float(hi[2]), float(-y)] for x, y in base]
+    quads = [[0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [3, 0, 4, 7], [0, 1, 2, 3]]
+    (ds / "scannet_planes" / f"{CLI_SCANS[0]}.json").write_text(json.dumps({"verts": verts, "quads": quads}))
+    return scenes

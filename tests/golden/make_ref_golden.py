@@ -274,6 +274,41 @@ def main():
     out["planes_json"], out["planes_align"] = np.array(plane_text), np.array(align_text)
     out["planes_cls"], out["planes_box"], out["planes_vol"] = np.asarray(wcls), np.asarray(wbox), np.asarray(wvol)
     print(f"wall boxes: {len(wbox)} of {len(quads)} quads kept")
+    # --- the CLI itself: gen_ps.py run as a script on a dataset/scannetv2 tree.  Environment stand-ins only: no GPU
+    # (.cuda() -> identity), torch.load of numpy pickles (weights_only default changed in torch 2.6), and the GP
+    # draws re-seeded per scan (hooked on get_wall_boxes, the call gen_ps.py makes once per scan before the labeler)
+    import pathlib
+    import runpy
+    from tests.golden.hand_cases import CLI_SCANS, cli_noise_seed, write_cli_dataset
+    real_walls, real_load, cuda = P.get_wall_boxes, torch.load, torch.Tensor.cuda
+
+    def walls_and_reseed(scan_name):
+        state["rng"] = np.random.default_rng(cli_noise_seed(scan_name))
+        return real_walls(scan_name)
+
+    with tempfile.TemporaryDirectory() as tmp:
+        write_cli_dataset(pathlib.Path(tmp))
+        os.makedirs(os.path.join(tmp, "out"))
+        torch.save(("sentinel",), os.path.join(tmp, "out", CLI_SCANS[1] + ".pth"))      # must be skipped (gen_ps.py:39-41)
+        P.get_wall_boxes = walls_and_reseed
+        torch.load = lambda f, *a, **k: real_load(f, *a, **{**k, "weights_only": False})
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        argv = sys.argv
+        sys.argv = ["gen_ps.py", "--save_folder", "out", "--eval_pslabel"]
+        os.chdir(tmp)
+        try:
+            runpy.run_path(os.path.join(REF, "gen_ps.py"), run_name="__main__")
+        finally:
+            os.chdir(cwd)
+            sys.argv = argv
+            P.get_wall_boxes, torch.load, torch.Tensor.cuda = real_walls, real_load, cuda
+        assert real_load(os.path.join(tmp, "out", CLI_SCANS[1] + ".pth"), weights_only=False) == ("sentinel",)
+        for scan in (CLI_SCANS[0], CLI_SCANS[2]):
+            tup = real_load(os.path.join(tmp, "out", scan + ".pth"), weights_only=False)
+            assert len(tup) == 5 and all(isinstance(a, np.ndarray) for a in tup)
+            for a, key in zip(tup, ("sem", "inst", "prob", "mu", "var")):
+                out[f"cli_{scan}_{key}"] = a
+            print(f"CLI {scan}: dtypes {[str(a.dtype) for a in tup]}, shapes {[a.shape for a in tup]}")
     np.savez_compressed(os.path.join(HERE, "ref_outputs.npz"), **out)
     print("wrote", os.path.join(HERE, "ref_outputs.npz"))
 

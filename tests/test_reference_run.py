@@ -134,6 +134,24 @@ def test_wall_boxes_equal_reference_run(ref, tmp_path):
     assert np.array_equal(np.asarray(box), ref["planes_box"]) and np.array_equal(np.asarray(vol), ref["planes_vol"])
 
 
+def test_host_io_and_oracle_equal_reference_cli_run(ref, tmp_path):
+    """The reference's gen_ps.py was executed as a script on this dataset tree (make_ref_golden.py); our loader
+    (disk layout, alignment, boxes, wall boxes from the planes file) feeding the oracle must reproduce the files it
+    saved, bit for bit."""
+    from gapro_b200.gen_ps import DATA_ROOT, load_scene
+    from oracle import gen_ps_oracle as O
+    from tests.golden.hand_cases import CLI_SCANS, cli_noise_seed, write_cli_dataset
+    write_cli_dataset(tmp_path)
+    root = tmp_path / DATA_ROOT
+    for scan in (CLI_SCANS[0], CLI_SCANS[2]):
+        inp, _, _ = load_scene(str(root / "train" / f"{scan}_inst_nostuff.pth"), scan, data_root=str(root))
+        assert (len(inp["wall_box"]) == 4) == (scan == CLI_SCANS[0])
+        res = O.gen_pseudo_label_oracle(*oracle_args(inp), thresh_spp_occu=0.999, noise_seed=cli_noise_seed(scan))
+        for got, key in zip(res, ("sem", "inst", "prob", "mu", "var")):
+            want = ref[f"cli_{scan}_{key}"]
+            assert got.dtype == want.dtype and np.array_equal(got, want), (scan, key)
+
+
 # ------------------------------------------------------------------------------------------------
 # CUDA path against the reference run
 # ------------------------------------------------------------------------------------------------
@@ -210,3 +228,29 @@ def test_cuda_equals_reference_run_on_hand_cases(dev, lib, ref, i, cname, thr):
 @pytest.mark.gpu
 def test_cuda_equals_reference_run_on_deep_features(dev, lib, ref):
     _check_cuda(_run_cuda(dev, _deep_inputs(), None, 11), ref, "deep")
+
+
+@pytest.mark.gpu
+def test_cuda_cli_equals_reference_cli_run(dev, lib, ref, tmp_path, monkeypatch):
+    """python -m gapro_b200.gen_ps against the files the reference's gen_ps.py script saved for the same dataset
+    tree: same names, same 5-tuple of numpy arrays (dtypes, shapes; mu / var per SUPERPOINT), the resume rule."""
+    from gapro_b200 import gen_ps
+    from tests.golden.hand_cases import CLI_SCANS, CLI_SEED, write_cli_dataset
+    write_cli_dataset(tmp_path)
+    monkeypatch.chdir(tmp_path)
+    for k, v in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")):
+        monkeypatch.setenv(k, v)
+    (tmp_path / "out").mkdir()
+    torch.save(("sentinel",), str(tmp_path / "out" / f"{CLI_SCANS[1]}.pth"))
+    gen_ps.main(["--save_folder", "out", "--seed", str(CLI_SEED), "--eval_pslabel"])
+    assert torch.load(str(tmp_path / "out" / f"{CLI_SCANS[1]}.pth"), weights_only=False) == ("sentinel",)
+    for scan in (CLI_SCANS[0], CLI_SCANS[2]):
+        tup = torch.load(str(tmp_path / "out" / f"{scan}.pth"), weights_only=False)
+        assert len(tup) == 5 and all(isinstance(a, np.ndarray) for a in tup)
+        for a, key in zip(tup, ("sem", "inst", "prob", "mu", "var")):
+            want = ref[f"cli_{scan}_{key}"]
+            assert a.dtype == want.dtype and a.shape == want.shape, (scan, key)
+            if key in ("sem", "inst"):
+                assert np.array_equal(a, want), (scan, key)
+            else:
+                assert np.allclose(a, want, rtol=1e-4, atol=1e-7), (scan, key)
