@@ -159,6 +159,11 @@ __device__ __forceinline__ int swz(int k) { return ((k >> 2) & 1) | (((k >> 3) &
 template <bool KC>
 __device__ __forceinline__ int frag_row(int i, int g) { return KC ? 8 * i + g : 4 * g + i; }
 
+// Which 32x32 quadrant of the tile a warp owns.  Warp w always runs on scheduler partition w mod 4, and
+// the quadrants do unequal work on triangular / padded tiles; rotating the assignment with the block
+// index spreads the lighter quadrants over all four partitions of an SM instead of always the same two.
+__device__ __forceinline__ int warp_quadrant() { return (int)((threadIdx.x >> 5) ^ (blockIdx.x & 3u)); }
+
 // Thread -> data map of the loaders: every warp-wide 16-byte cp.async lands on distinct banks
 // (k-contiguous tile: 4 rows x 8 units, bank = (row + unit) mod 8 with the 9-unit row stride;
 //  r-contiguous tile: one k-row x 32 units, XOR-swizzle permutes banks inside each group of 8).
@@ -210,16 +215,21 @@ __device__ __forceinline__ void load_frags(double (&f)[4][2], const double* s, i
 // acc[i][j][e] holds C(row, col) with row = wm*32 + frag_row<AKC>(i, gid),
 //                                      col = wn*32 + frag_row<BKC>(j, 2*tig + e)
 // Three-stage cp.async pipeline, one __syncthreads per 16-deep chunk.
-template <bool AKC, bool BKC>
+template <bool AKC, bool BKC, int TRI = 0>
 __device__ __forceinline__ void gemm_accum(double (&acc)[4][4][2], const double* __restrict__ A, int lda,
                                            const double* __restrict__ B, int ldb, int k0, int k1,
                                            const double* __restrict__ kscale, GemmSmem& sm, int mlim = TB,
-                                           int nlim = TB) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                           int nlim = TB, int tri0 = 0) {
+    const int lane = threadIdx.x & 31, warp = warp_quadrant();
     const int gid = lane >> 2, tig = lane & 3;
     const int wm32 = (warp >> 1) * 32, wn32 = (warp & 1) * 32;
     // a warp whose 32x32 block lies entirely in the zero padding only helps with the loads
     const bool active = wm32 < mlim && wn32 < nlim;
+    // triangular operand: the warp's 32 rows (TRI = +-1, A operand) or columns (TRI = 2, B operand) see only
+    // zeros beyond / before the diagonal, so it may skip those chunks (tri0 = first row / column of the tile)
+    //   TRI = +1: A(r,k) = 0 for k > r      TRI = -1: A(r,k) = 0 for k < r      TRI = 2: B(c,k) = 0 for k < c
+    const int wk_hi = TRI == 1 ? tri0 + wm32 + 32 : 0x7fffffff;
+    const int wk_lo = TRI == -1 ? tri0 + wm32 : (TRI == 2 ? tri0 + wn32 : 0);
     const int nchunk = (k1 - k0) / BK;
     if (nchunk <= 0) return;
 #pragma unroll
@@ -252,9 +262,14 @@ __device__ __forceinline__ void gemm_accum(double (&acc)[4][4][2], const double*
         }
         const double* sa = sm.a[stage];
         const double* sb = sm.b[stage];
+        bool on = active;
+        if (TRI != 0) {
+            const int kc = k0 + c * BK;
+            on = on && kc < wk_hi && kc + BK > wk_lo;
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            if (!active) break;
+            if (!on) break;
             double af[4][2], bf[4][2];
             load_frags<AKC>(af, sa, wm32, gid, tig, h);
             load_frags<BKC>(bf, sb, wn32, gid, tig, h);
@@ -282,7 +297,7 @@ __device__ __forceinline__ void gemm_accum(double (&acc)[4][4][2], const double*
 // Visits the accumulator as pairs of horizontally adjacent elements: v0 = C(row, col), v1 = C(row, col+1).
 #define ACC_FOREACH(AKC_, BKC_, ROW0, COL0, ...)                                                   \
     {                                                                                              \
-        const int lane_ = threadIdx.x & 31, warp_ = threadIdx.x >> 5;                              \
+        const int lane_ = threadIdx.x & 31, warp_ = warp_quadrant();                               \
         const int gid_ = lane_ >> 2, tig_ = lane_ & 3;                                             \
         const int wm_ = warp_ >> 1, wn_ = warp_ & 1;                                               \
         _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                                         \
@@ -327,17 +342,18 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
 #define KCLIP(k) ((k) < kend ? (k) : kend)
 
     if (PH == PH_A) {          // A = Linv * Kzx, Linv lower: k <= i
-        gemm_accum<true, false>(acc, base + lay.Linv + (size_t)r0 * Mp, Mp, base + lay.Kzx + c0, Wp, 0, KCLIP(r0 + TB),
-                                nullptr, sm, mlim, nlim);
+        gemm_accum<true, false, 1>(acc, base + lay.Linv + (size_t)r0 * Mp, Mp, base + lay.Kzx + c0, Wp, 0,
+                                   KCLIP(r0 + TB), nullptr, sm, mlim, nlim, r0);
         double* out = base + lay.A;
         ACC_FOREACH(true, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
     } else if (PH == PH_B) {   // B = T^T * A, T lower: k >= i
-        gemm_accum<false, false>(acc, base + lay.T + r0, Mp, base + lay.A + c0, Wp, r0, kend, nullptr, sm, mlim, nlim);
+        gemm_accum<false, false, -1>(acc, base + lay.T + r0, Mp, base + lay.A + c0, Wp, r0, kend, nullptr, sm, mlim,
+                                     nlim, r0);
         double* out = base + lay.Bm;
         ACC_FOREACH(false, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1); })
     } else if (PH == PH_GA) {  // G_A = m g_mu^T + 2 (T B - A) diag(g_v)
-        gemm_accum<true, false>(acc, base + lay.T + (size_t)r0 * Mp, Mp, base + lay.Bm + c0, Wp, 0, KCLIP(r0 + TB), nullptr,
-                                sm, mlim, nlim);
+        gemm_accum<true, false, 1>(acc, base + lay.T + (size_t)r0 * Mp, Mp, base + lay.Bm + c0, Wp, 0, KCLIP(r0 + TB),
+                                   nullptr, sm, mlim, nlim, r0);
         const double* Am = base + lay.A;
         const double* mv = base + lay.m;
         const double* gmu = base + lay.gmu;
@@ -374,7 +390,8 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
             }
         })
     } else if (PH == PH_GC) {  // G_C = Linv^T * G_A: k >= i
-        gemm_accum<false, false>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, kend, nullptr, sm, mlim, nlim);
+        gemm_accum<false, false, -1>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, kend, nullptr, sm, mlim,
+                                     nlim, r0);
         double* out = base + lay.GC;
         ACC_FOREACH(false, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = make_double2(v0, v1); })
     } else if (PH == PH_GL) {
@@ -396,12 +413,13 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
             }
         })
     } else if (PH == PH_Y) {   // Y = S * Linv: k >= j   (into the G_A buffer)
-        gemm_accum<true, false>(acc, base + lay.Bm + (size_t)r0 * Wp, Wp, base + lay.Linv + c0, Mp, c0, kend, nullptr,
-                                sm, mlim, nlim);
+        gemm_accum<true, false, 2>(acc, base + lay.Bm + (size_t)r0 * Wp, Wp, base + lay.Linv + c0, Mp, c0, kend, nullptr,
+                                   sm, mlim, nlim, c0);
         double* out = base + lay.GA;
         ACC_FOREACH(true, false, r0, c0, { *reinterpret_cast<double2*>(out + (size_t)row * Mp + col) = make_double2(v0, v1); })
     } else if (PH == PH_GK) {  // G_K = Linv^T * Y (symmetric): lower tiles, mirrored   (into the B buffer)
-        gemm_accum<false, false>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, kend, nullptr, sm, mlim, nlim);
+        gemm_accum<false, false, -1>(acc, base + lay.Linv + r0, Mp, base + lay.GA + c0, Mp, r0, kend, nullptr, sm, mlim,
+                                     nlim, r0);
         double* out = base + lay.Bm;
         ACC_FOREACH(false, false, r0, c0, {
             *reinterpret_cast<double2*>(out + (size_t)row * Wp + col) = make_double2(v0, v1);
