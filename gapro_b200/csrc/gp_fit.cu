@@ -15,6 +15,7 @@
 // All O(M^3) products run on the FP64 tensor pipe (mma.sync m8n8k4 f64, "DMMA") from shared
 // memory tiles filled by cp.async double buffering.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -885,16 +886,27 @@ k_grad_m(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPar
 }
 
 // Gradients w.r.t. the inducing points and the raw kernel parameters from G_K (in the B buffer,
-// symmetric) and G_C.  A CTA owns 8*ROWS inducing rows (ROWS per warp); the Z / X rows of the
-// current block of 32 columns are staged once per CTA in shared memory (transposed, conflict-free),
-// lanes run over the 32 columns and the four matrix rows are read coalesced.
+// symmetric) and G_C.  A CTA owns 8*ROWS inducing rows (ROWS per warp) and walks over the columns in
+// blocks of 32.  HBM-bound (four M x M matrices are read once): the 32 x 32 blocks of the four matrices
+// and the Z / X rows of the column block are staged by a three-stage cp.async pipeline (one
+// __syncthreads per block, two blocks always in flight), lanes run over the 32 columns.
+constexpr int KG_STAGES = 3;
+template <int DMAX>
+struct KgStage {
+    double gk[32][32], kz[32][32], gc[32][32], kx[32][32];   // G_K, K_zz, G_C, K_zx blocks
+    double z[32 * DMAX], x[32 * DMAX];                       // rows jb..jb+31 of Z and X, [32][D] as in memory
+};
+template <int DMAX, int ROWS>
+constexpr int kgrad_smem() { return KG_STAGES * (int)sizeof(KgStage<DMAX>) + 8 * ROWS * DMAX * (int)sizeof(double); }
+
 template <int DMAX, int ROWS>
 __global__ void __launch_bounds__(256, (DMAX <= 8) ? 2 : 1)
 k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpParams prm, double* __restrict__ ws) {
+    static_assert(8 * ROWS == 32, "one CTA stages 32 matrix rows");
     constexpr int SPLIT = TB / (8 * ROWS);           // CTAs per 64-row tile
-    __shared__ double Zs[DMAX][33];
-    __shared__ double Xs[DMAX][33];
-    __shared__ double Zi[8 * ROWS][DMAX];
+    extern __shared__ __align__(16) unsigned char smem_kg[];
+    KgStage<DMAX>* st = reinterpret_cast<KgStage<DMAX>*>(smem_kg);
+    double (*Zi)[DMAX] = reinterpret_cast<double (*)[DMAX]>(smem_kg + KG_STAGES * sizeof(KgStage<DMAX>));
     const int2 rt = rtiles[blockIdx.x / SPLIT];
     const Region R = regs[rt.x];
     const int D = prm.D;
@@ -912,6 +924,29 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
         const int rr = e / DMAX, d = e - rr * DMAX;
         Zi[rr][d] = (d < D && row0 + rr < R.M) ? Z[(size_t)(row0 + rr) * D + d] : 0.0;
     }
+    // loader: thread t moves 16-byte unit (t & 15) of row (t >> 4) + 16 * (q & 1) of matrix q >> 1, q = 0..7
+    // (rows row0 .. row0+31 and columns jb .. jb+31 always exist: the matrices are padded to multiples of 64)
+    const int lr = threadIdx.x >> 4, lc = 2 * (threadIdx.x & 15);
+    const double* g_gk = base + lay.Bm + (size_t)(row0 + lr) * R.Wp + lc;
+    const double* g_kz = base + lay.Kc + (size_t)(row0 + lr) * R.Mp + lc;
+    const double* g_gc = base + lay.GC + (size_t)(row0 + lr) * R.Mp + lc;
+    const double* g_kx = base + lay.Kzx + (size_t)(row0 + lr) * R.Wp + lc;
+    const size_t half_w = (size_t)16 * R.Wp, half_m = (size_t)16 * R.Mp;
+    const int zx_units = 16 * D;                     // 16-byte units in 32 rows of Z (or X)
+    auto issue = [&](int stage, int jb) {
+        KgStage<DMAX>& S = st[stage];
+        cp_async16(&S.gk[lr][lc], g_gk + jb);
+        cp_async16(&S.gk[lr + 16][lc], g_gk + half_w + jb);
+        cp_async16(&S.kz[lr][lc], g_kz + jb);
+        cp_async16(&S.kz[lr + 16][lc], g_kz + half_m + jb);
+        cp_async16(&S.gc[lr][lc], g_gc + jb);
+        cp_async16(&S.gc[lr + 16][lc], g_gc + half_m + jb);
+        cp_async16(&S.kx[lr][lc], g_kx + jb);
+        cp_async16(&S.kx[lr + 16][lc], g_kx + half_w + jb);
+        const int t = threadIdx.x;
+        if (t < zx_units) cp_async16(&S.z[2 * t], Z + (size_t)jb * D + 2 * t);
+        else if (t < 2 * zx_units) cp_async16(&S.x[2 * (t - zx_units)], X + (size_t)jb * D + 2 * (t - zx_units));
+    };
     double az[ROWS][DMAX], as[ROWS], al[ROWS], cz[ROWS];
 #pragma unroll
     for (int q = 0; q < ROWS; ++q) {
@@ -919,26 +954,35 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
 #pragma unroll
         for (int d = 0; d < DMAX; ++d) az[q][d] = 0.0;
     }
-    for (int jb = 0; jb < R.M; jb += 32) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < 32 * D; e += blockDim.x) {     // coalesced: rows jb..jb+31 are contiguous
-            const int jj = e / D, d = e - jj * D;
-            const bool ok = jb + jj < R.M;
-            Zs[d][jj] = ok ? Z[(size_t)jb * D + e] : 0.0;
-            Xs[d][jj] = ok ? X[(size_t)jb * D + e] : 0.0;
+    const int nblk = (R.M + 31) >> 5;
+#pragma unroll
+    for (int p = 0; p < KG_STAGES - 1; ++p) {
+        if (p < nblk) issue(p, 32 * p);
+        cp_async_commit();
+    }
+    int stage = 0;
+    for (int b = 0; b < nblk; ++b) {
+        cp_async_wait<KG_STAGES - 2>();   // block b has landed
+        __syncthreads();                  // ... for every thread, block b-1 is consumed, Zi is visible
+        {
+            const int nb = b + KG_STAGES - 1;
+            int ns = stage + KG_STAGES - 1;
+            if (ns >= KG_STAGES) ns -= KG_STAGES;
+            if (nb < nblk) issue(ns, 32 * nb);
+            cp_async_commit();
         }
-        __syncthreads();
-        const int j = jb + lane;
+        const KgStage<DMAX>& S = st[stage];
+        const int j = 32 * b + lane;
         if (j < R.M) {
             // the adjoint weights do not depend on the distances: read them first, then ONE pass over d
             double grz2[ROWS], grx[ROWS], d2z[ROWS], d2x[ROWS];
 #pragma unroll
             for (int q = 0; q < ROWS; ++q) {
-                const int i = row0 + warp * ROWS + q;
+                const int r = warp * ROWS + q;
                 grz2[q] = grx[q] = d2z[q] = d2x[q] = 0.0;
-                if (i < R.M) {
-                    const double gk = base[lay.Bm + (size_t)i * R.Wp + j], kz = base[lay.Kc + (size_t)i * R.Mp + j];
-                    const double gc = base[lay.GC + (size_t)i * R.Mp + j], kx = base[lay.Kzx + (size_t)i * R.Wp + j];
+                if (row0 + r < R.M) {
+                    const double gk = S.gk[r][lane], kz = S.kz[r][lane];
+                    const double gc = S.gc[r][lane], kx = S.kx[r][lane];
                     // zz: W = Gr + Gr^T = 2 Gr (G_K, K_zz symmetric);  zx: Gr once.
                     // sum_j [2 grz (z_i - z_j) + grx (z_i - x_j)] = z_i * cz - sum_j (2 grz z_j + grx x_j)
                     grz2[q] = -gk * kz;
@@ -950,7 +994,7 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
 #pragma unroll
             for (int d = 0; d < DMAX; ++d) {
                 if (d < D) {
-                    const double zjd = Zs[d][lane], xjd = Xs[d][lane];
+                    const double zjd = S.z[lane * D + d], xjd = S.x[lane * D + d];
 #pragma unroll
                     for (int q = 0; q < ROWS; ++q) {
                         const double zi = Zi[warp * ROWS + q][d];
@@ -964,7 +1008,9 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
 #pragma unroll
             for (int q = 0; q < ROWS; ++q) al[q] += (0.5 * grz2[q] * d2z[q] + grx[q] * d2x[q]) * (inv_l2 * m2_ell);
         }
+        if (++stage == KG_STAGES) stage = 0;
     }
+    cp_async_wait<0>();
 #pragma unroll
     for (int q = 0; q < ROWS; ++q) {
         const int i = row0 + warp * ROWS + q;
@@ -1224,9 +1270,10 @@ struct ChunkTables {
 // ---- opt-in per-phase profiling with CUDA events on the launching stream ------------------
 constexpr int PROF_PREDICT = PH_COUNT, PROF_SETUP = PH_COUNT + 1, PROF_SLOTS = PH_COUNT + 2;
 struct ProfSpan {
-    int slot;
+    int slot, group;
     cudaEvent_t a, b;
 };
+thread_local int g_prof_group = 0;
 struct ProfState {
     bool on = false;
     std::vector<ProfSpan> spans;
@@ -1240,6 +1287,7 @@ void prof_begin(int slot, cudaStream_t st) {
     if (!g_prof.on) return;
     ProfSpan sp;
     sp.slot = slot;
+    sp.group = g_prof_group;
     cudaEventCreate(&sp.a);
     cudaEventCreate(&sp.b);
     cudaEventRecord(sp.a, st);
@@ -1353,8 +1401,10 @@ struct Driver {
     }
 
     void kgrad(const GpParams& p) {
-        if (D <= 8)
-            k_kgrad<8, 4><<<tb.n_rows * 2, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+        if (D <= 6)
+            k_kgrad<6, 4><<<tb.n_rows * 2, 256, kgrad_smem<6, 4>(), stream>>>(tb.regs, tb.rows, p, ws);
+        else if (D <= 8)
+            k_kgrad<8, 4><<<tb.n_rows * 2, 256, kgrad_smem<8, 4>(), stream>>>(tb.regs, tb.rows, p, ws);
         else if (D <= 32)
             k_kgrad_wide<1><<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         else
@@ -1559,7 +1609,8 @@ static int n_groups_for(size_t n_regions) {
     if (const char* e = getenv("GAPRO_GP_STREAMS")) g = atoi(e);
     if (g < 1) g = 1;
     if (g > MAX_GROUPS) g = MAX_GROUPS;
-    if (g_prof.on) g = 1;                       // per-phase event timing needs a single stream
+    // per-phase event timing needs a single stream (GAPRO_GP_TIMELINE keeps the groups: overlapping spans)
+    if (g_prof.on && !getenv("GAPRO_GP_TIMELINE")) g = 1;
     while (g > 1 && n_regions < (size_t)4 * g) --g;
     return g;
 }
@@ -1589,12 +1640,13 @@ static int set_kernel_attributes() {
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GL>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_Y>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GK>, GEMM_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<6, 4>, kgrad_smem<6, 4>());
+    if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<8, 4>, kgrad_smem<8, 4>());
     if (!getenv("GAPRO_GP_DEFAULT_CARVEOUT")) {
         // the element-wise kernels too: a kernel that prefers a large L1 cannot share an SM with the tile
         // kernels of another group, which would serialise the side streams
         if (rc == GAPRO_OK) rc = allow_smem(k_colstats, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_grad_m, 0);
-        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<8, 4>, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_kgrad_wide<1>, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_kgrad_wide<2>, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_adam_small, 0);
@@ -1680,7 +1732,11 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
         prof_end(stream);
         for (const Region& r : chunk) prof_account_train(r, iters);
         for (int it = 1; it <= iters; ++it)
-            for (int g = 0; g < G; ++g) drv[g].train_step(it, PH_COUNT);
+            for (int g = 0; g < G; ++g) {
+                g_prof_group = g;
+                drv[g].train_step(it, PH_COUNT);
+            }
+        g_prof_group = 0;
         if (stop_phase > 0)
             for (int g = 0; g < G; ++g) drv[g].train_step(iters + 1, stop_phase);
         if (do_predict)
@@ -1755,6 +1811,18 @@ extern "C" int gapro_gp_get_profile(double* ms, double* flops_alg, double* flops
         float t = 0.f;
         GAPRO_CUDA_TRY(cudaEventElapsedTime(&t, sp.a, sp.b));
         ms[sp.slot] += t;
+    }
+    if (const char* path = getenv("GAPRO_GP_TIMELINE")) {
+        // development aid: every span as "slot group start_ms end_ms" relative to the first one
+        if (FILE* f = fopen(path, "w")) {
+            for (ProfSpan& sp : g_prof.spans) {
+                float t0 = 0.f, t1 = 0.f;
+                cudaEventElapsedTime(&t0, g_prof.spans.front().a, sp.a);
+                cudaEventElapsedTime(&t1, g_prof.spans.front().a, sp.b);
+                fprintf(f, "%d %d %.4f %.4f\n", sp.slot, sp.group, t0, t1);
+            }
+            fclose(f);
+        }
     }
     return PROF_SLOTS;
 }
