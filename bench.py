@@ -244,6 +244,27 @@ def stage_rooflines(eng, lib, stream, flush):
     return out
 
 
+PHASE_ID = {"A": 2, "B": 3, "GA": 5, "GT": 6, "GC": 8, "GL": 9, "Y": 11, "GK": 12}
+
+
+def ncu_traffic(phase, args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/r01_traffic.json, written by profiles/summarize.py);
+    null when the capture is of another workload."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+    except OSError:
+        return None, "no ncu capture committed"
+    if t.get("workload") != f"{args.workload} x {args.scenes}":
+        return None, f"committed capture is of '{t.get('workload')}'"
+    k = t["kernels"].get(f"k_gemm<{PHASE_ID.get(phase, -1)}>")
+    if not k:
+        return None, "kernel not in the committed capture"
+    return k["dram_read_bytes"] + k["dram_write_bytes"], f"profiles/r01_traffic.json ({t.get('command', 'ncu --set full')})"
+
+
 def run_gpu(args):
     rank, world, local = dist_env()
     import torch.distributed as dist
@@ -389,6 +410,7 @@ def run_gpu(args):
                         "frac_issued": fam_exe / (fam_ms * 1e-3) / peak},
         "gp_stage_ms": gp_ms, "phases_ms": {n: round(phases[n]["ms"], 3) for n in names},
     }
+    roofline["traffic"], roofline["traffic_source"] = ncu_traffic(top, args)
     stages = stage_rooflines(eng, lib, stream, flush)
     # the same kernels on a batch large enough to amortise launch latency (the step's scenes, 8 times over)
     eng.run(scenes * 8, stages_only=True, **kw)

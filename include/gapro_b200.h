@@ -211,6 +211,9 @@ int gapro_compact_lists(const uint32_t* occ_bits, const int32_t* n_bbs, const in
  *   status     dev int32[n_regions]  out: GAPRO_GP_* bits
  * The workspace may be smaller than gapro_gp_workspace_bytes(); regions are
  * then processed in as many chunks as needed (minimum: the largest region).
+ * Asynchronous on `stream`, except that the host tile tables of every workspace chunk are uploaded and the
+ * stream is synchronised once per chunk before its kernels are enqueued (one chunk unless ws_bytes is smaller than
+ * gapro_gp_workspace_bytes).
  */
 size_t gapro_gp_workspace_bytes(int32_t n_regions, const int32_t* train_off, const int32_t* test_off, int32_t D);
 size_t gapro_gp_min_workspace_bytes(int32_t n_regions, const int32_t* train_off, const int32_t* test_off,
