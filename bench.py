@@ -231,6 +231,13 @@ def stage_rooflines(eng, lib, stream, flush):
     bc = lambda: _lib.check(lib.gapro_broadcast_labels(L["spp_gid"].data_ptr(), N, L["packed_spp"].data_ptr(),
                                                        L["sem"].data_ptr(), L["inst"].data_ptr(), L["prob"].data_ptr(),
                                                        stream), "bcast")
+    # the gather wall: the same number of 24-byte records read at random addresses and nothing else
+    gidx = torch.randperm(N, device=L["xyz"].device, dtype=torch.int32)
+    sink = torch.zeros(1, dtype=torch.float64, device=L["xyz"].device)
+    gather = lambda: _lib.check(lib.gapro_gather_peak(gidx.data_ptr(), L["xyz"].data_ptr(), N, sink.data_ptr(), stream),
+                                "gather")
+    g_ms = time_it(gather)
+    g_gbs = N * 28 / (g_ms * 1e-3) / 1e9
     out = {}
     for name, fn, nbytes in (
         ("containment+occupancy (A+A')", occ, N * (24 + 4) + 48 * Bt + 4 * S * words + 4 * S),
@@ -241,6 +248,13 @@ def stage_rooflines(eng, lib, stream, flush):
         gbs = nbytes / (ms * 1e-3) / 1e9
         out[name] = {"ms": ms, "algorithmic_bytes": int(nbytes), "achieved": gbs, "peak": peak, "unit": "GB/s",
                      "frac": gbs / peak, "peak_source": peak_src}
+    for name in ("containment+occupancy (A+A')", "feature pooling (B)"):
+        # both read N random 24-byte records + a coalesced index: the random-gather microbenchmark is their roofline
+        out[name]["random_gather_peak"] = g_gbs
+        out[name]["frac_of_random_gather_peak"] = out[name]["achieved"] / g_gbs
+    out["random 24-byte gather microbenchmark (gapro_gather_peak)"] = {
+        "ms": g_ms, "algorithmic_bytes": int(N * 28), "achieved": g_gbs, "peak": peak, "unit": "GB/s",
+        "frac": g_gbs / peak, "peak_source": peak_src}
     return out
 
 

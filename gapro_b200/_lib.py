@@ -43,6 +43,7 @@ _SIGNATURES = {
     "gapro_gp_phase_names": (c_char_p, []),
     "gapro_gp_get_profile": (ctypes.c_int, [P, P, P, c_int32]),
     "gapro_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, P, P, P]),
+    "gapro_gather_peak": (ctypes.c_int, [P, P, c_int64, P, P]),
     "gapro_gp_debug_run": (ctypes.c_int, [P, c_int32, c_int32, c_int32, c_int32, P, P, P, c_int32, c_int32,
                                           c_double, c_double, c_double, P, c_size_t, P, c_int32, P]),
     "gapro_gp_debug_layout_names": (c_char_p, []),

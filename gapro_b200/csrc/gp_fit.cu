@@ -1851,9 +1851,35 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
     for (int j = 0; j < 8; ++j) s += acc[j][0] + acc[j][1];
     if (s == 12345.678) out[0] = s;
 }
+
+// both at once: 4 DMMA (1024 FMA per warp) and 32 DFMA (1024 FMA per warp) per iteration, independent
+// accumulators - do the tensor sub-pipe and the FP64 FMA pipe add up, or do they share the datapath?
+__global__ void __launch_bounds__(256) k_fp64_peak_mixed(double* out, int iters) {
+    double acc[4][2], f[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = 0.0;
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) dmma(acc[2 * r + j][0], acc[2 * r + j][1], a, b);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fma(a, b, f[j]);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += acc[j][0] + acc[j][1];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += f[j];
+    if (s == 12345.678) out[0] = s;
+}
 }  // namespace
 
-// Returns the sustained FP64 rate in TFLOP/s of a register-resident DMMA (use_dmma=1) or DFMA loop.
+// Returns the sustained FP64 rate in TFLOP/s of a register-resident DMMA (use_dmma=1), DFMA (0) or mixed (2) loop.
 extern "C" int gapro_fp64_peak(int use_dmma, int iters, double* tflops, double* scratch_dev, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GAPRO_REQUIRE(tflops && scratch_dev && iters > 0, "gapro_fp64_peak: bad arguments");
@@ -1866,7 +1892,9 @@ extern "C" int gapro_fp64_peak(int use_dmma, int iters, double* tflops, double* 
     GAPRO_CUDA_TRY(cudaEventCreate(&b));
     for (int rep = 0; rep < 2; ++rep) {   // first pass warms up
         GAPRO_CUDA_TRY(cudaEventRecord(a, stream));
-        if (use_dmma)
+        if (use_dmma == 2)
+            k_fp64_peak_mixed<<<blocks, threads, 0, stream>>>(scratch_dev, iters);
+        else if (use_dmma)
             k_fp64_peak<true><<<blocks, threads, 0, stream>>>(scratch_dev, iters);
         else
             k_fp64_peak<false><<<blocks, threads, 0, stream>>>(scratch_dev, iters);
@@ -1878,7 +1906,8 @@ extern "C" int gapro_fp64_peak(int use_dmma, int iters, double* tflops, double* 
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     // DMMA m8n8k4: 256 FMA per warp instruction; DFMA: 2 per thread per j
-    const double fma_per_block_iter = use_dmma ? (threads / 32) * 8.0 * 256.0 : threads * 8.0 * 2.0;
+    const double fma_per_block_iter = use_dmma == 2 ? (threads / 32) * 2048.0
+                                      : use_dmma  ? (threads / 32) * 8.0 * 256.0 : threads * 8.0 * 2.0;
     *tflops = 2.0 * fma_per_block_iter * blocks * (double)iters / (ms * 1e-3) / 1e12;
     return GAPRO_OK;
 }

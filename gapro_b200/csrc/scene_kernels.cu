@@ -1064,3 +1064,34 @@ extern "C" int gapro_broadcast_labels(const int32_t* spp_gid, int64_t n_points, 
     GAPRO_KERNEL_CHECK();
     return GAPRO_OK;
 }
+
+// =============================================================================================
+// Random-gather microbenchmark: the roofline of the gather-bound stages.  k_occupancy and k_pool_feats read
+// every point once, but through `perm` (points grouped by superpoint), i.e. as 24-byte records at random
+// addresses.  This kernel does nothing else: coalesced index read, one independent 24-byte gather per
+// record (4 records per thread in flight), a sum that is never stored.  Timed by the caller (bench.py).
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+k_gather_peak(const int32_t* __restrict__ idx, const double* __restrict__ table, int64_t n, double* __restrict__ sink) {
+    const int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    int64_t p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t k = base + 256 * i;
+        p[i] = k < n ? (int64_t)idx[k] : -1;
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (p[i] >= 0) s += table[3 * p[i]] + table[3 * p[i] + 1] + table[3 * p[i] + 2];
+    if (s == 1.2345e300) sink[0] = s;      // keeps the loads alive
+}
+
+extern "C" int gapro_gather_peak(const int32_t* idx, const double* table, int64_t n_records, double* sink,
+                                 void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GAPRO_REQUIRE(idx && table && sink && n_records > 0, "gapro_gather_peak: bad arguments");
+    k_gather_peak<<<(unsigned)((n_records + 1023) / 1024), 256, 0, stream>>>(idx, table, n_records, sink);
+    GAPRO_KERNEL_CHECK();
+    return GAPRO_OK;
+}

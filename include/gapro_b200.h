@@ -240,6 +240,12 @@ int gapro_gp_get_profile(double* ms, double* flops_alg, double* flops_exe, int32
  * (MEASURED_PEAKS.json has no FP64 figure).  scratch_dev: dev double[1].  SYNCHRONISES. */
 int gapro_fp64_peak(int use_dmma, int iters, double* tflops, double* scratch_dev, void* stream);
 
+/* Random-gather microbenchmark (the roofline of the gather-bound stages A/A' and B): one launch reads
+ * idx[0..n_records) coalesced and gathers the 24-byte record table[3*idx[i] .. +3) for each; nothing is
+ * written.  The caller times the launch (bench.py: CUDA events, L2 flushed) and reports
+ * n_records * 28 bytes / time next to the copy bandwidth.  idx dev int32[n_records], table dev double[>= 3*(max idx+1)]. */
+int gapro_gather_peak(const int32_t* idx, const double* table, int64_t n_records, double* sink, void* stream);
+
 /* Debug/test hook: run ONE region for `iters` full steps plus the first
  * `stop_phase` phases of the next step, no prediction, and leave the workspace
  * as is.  layout receives the offsets (in doubles) of the region's buffers in
