@@ -140,7 +140,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": n_workers, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -257,6 +257,8 @@ def stage_rooflines(eng, lib, stream, flush):
         "frac": g_gbs / peak, "peak_source": peak_src}
     return out
 
+
+_RESULT_OUT = sys.stdout
 
 PHASE_ID = {"A": 2, "B": 3, "GA": 5, "GT": 6, "GC": 8, "GL": 9, "Y": 11, "GK": 12}
 
@@ -463,7 +465,7 @@ def run_gpu(args):
         "clocks": clocks, "roofline": roofline, "stage_rooflines": stages, "stage_rooflines_large_batch": stages_large,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -478,6 +480,12 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c1_deep", "c4", "c5", "small", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON); whatever libraries print there (NCCL prints its version banner
+    # to stdout at communicator creation) goes to stderr instead
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         os.environ["CUDA_VISIBLE_DEVICES"] = ""       # CPU arm: keep forked workers away from CUDA
         run_reference(args)
