@@ -413,7 +413,7 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
                 }
             }
         })
-    } else if (PH == PH_Y) {   // Y = S * Linv: k >= j   (into the G_A buffer)
+    } else if (PH == PH_Y) {   // Y = S * Linv: k >= j, lower tiles only (all that G_K's lower tiles read; into the G_A buffer)
         gemm_accum<true, false, 2>(acc, base + lay.Bm + (size_t)r0 * Wp, Wp, base + lay.Linv + c0, Mp, c0, kend, nullptr,
                                    sm, mlim, nlim, c0);
         double* out = base + lay.GA;
@@ -1315,7 +1315,7 @@ void prof_account_train(const Region& r, int steps) {
     add(PH_GT, m3, t3 * tri * nb);
     add(PH_GC, m3, kfull_tri);
     add(PH_GL, m3, t3 * tri * nb);
-    add(PH_Y, m3, kfull_tri);
+    add(PH_Y, 2.0 * m3 / 3.0, t3 * nb * (nb + 1) * (2 * nb + 1) / 6.0);
     add(PH_GK, m3 / 3.0, t3 * nb * (nb + 1) * (nb + 2) / 6.0);
     (void)Mp;
 }
@@ -1436,7 +1436,7 @@ struct Driver {
         PHASE(gemm<PH_GC>(tb.full, tb.n_full, p))
         PHASE(gemm<PH_GL>(tb.lower, tb.n_lower, p))
         PHASE((void)0)   // (slot of the former L^T G_L product, folded into the previous phase)
-        PHASE(gemm<PH_Y>(tb.full, tb.n_full, p))
+        PHASE(gemm<PH_Y>(tb.lower, tb.n_lower, p))   // G_K's lower tiles read only Y[k >= j]
         PHASE(gemm<PH_GK>(tb.lower, tb.n_lower, p))
         PHASE(kgrad(p))
         PHASE((k_adam_small<<<n_regs, 256, 0, stream>>>(tb.regs, p, ws), ++g_launches))

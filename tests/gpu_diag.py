@@ -140,7 +140,7 @@ def section_phases():
     s = st(ph["GL"] + 1)
     print("  symP:", rel(s["Bm"][:M, :M], it["symP"]))
     s = st(ph["Y"] + 1)
-    print("  Y:", rel(s["GA"][:M, :M], it["symP"] @ it["Linv"]))
+    print("  Y (lower tiles):", rel(np.tril(s["GA"][:M, :M]), np.tril(it["symP"] @ it["Linv"])))
     s = st(ph["GK"] + 1)
     print("  G_K:", rel(s["Bm"][:M, :M], it["G_K"]))
     s = st(ph["kgrad"] + 1)
