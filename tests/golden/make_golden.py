@@ -21,6 +21,8 @@ from oracle import gen_ps_oracle as O                  # noqa: E402
 from oracle import gp_oracle as G                      # noqa: E402
 
 GP_CASES = [(2, 6, 1), (3, 6, 4), (17, 6, 9), (64, 6, 30), (65, 6, 70), (96, 32, 12), (150, 6, 20)]
+# sizes of the real workload (16 blocks of 64, deep features): golden vectors only, the CPU suite re-derives the first
+GP_CASES_LARGE = [(200, 6, 40), (1000, 6, 64), (520, 32, 48)]
 
 
 def gp_case(i, M, D, N):
@@ -57,6 +59,14 @@ def main():
         out[f"c{i}_label"], out[f"c{i}_conf"] = r["label"], r["conf"]
         print(f"gp case {i}: M={M} D={D} N={N} mu[0]={r['mu64'][0]:.6f}")
     np.savez_compressed(os.path.join(HERE, "gp_cases.npz"), **out)
+    out = {}
+    for i, (M, D, N) in enumerate(GP_CASES_LARGE):
+        X, n1, Xt, noise = gp_case(100 + i, M, D, N)
+        r = G.fit_region_autograd(X, n1, Xt, noise)
+        out[f"c{i}_mu64"], out[f"c{i}_var64"], out[f"c{i}_prob"] = r["mu64"], r["var64"], r["prob"]
+        out[f"c{i}_label"], out[f"c{i}_conf"] = r["label"], r["conf"]
+        print(f"large gp case {i}: M={M} D={D} N={N} mu[0]={r['mu64'][0]:.6f} min margin {np.abs(r['prob64'] - 0.5).min():.3g}")
+    np.savez_compressed(os.path.join(HERE, "gp_cases_large.npz"), **out)
     for name, seed, nseed in [("tiny", 3, 5), ("small", 4, 6)]:
         inp, args = scene_inputs(name, seed)
         res, dbg = O.gen_pseudo_label_oracle(*args, thresh_spp_occu=0.999, noise_seed=nseed, return_debug=True)

@@ -203,6 +203,21 @@ def test_gp_fits_match_golden_vectors(dev, lib):
             assert r[0].dtype == torch.float32 and r[2].dtype == torch.bool and r[3].dtype == torch.float32
 
 
+def test_gp_fits_match_golden_vectors_at_workload_sizes(dev, lib):
+    """M = 200, 1000 (16 blocks of 64: even / odd block steps, merged updates), 520 with 32-d features."""
+    from gapro_b200.gaussian_process_utils import fit_gp_regions
+    from tests.golden.make_golden import GP_CASES_LARGE
+    gold = np.load(os.path.join(GOLD_DIR, "gp_cases_large.npz"))
+    for i, (M, D, N) in enumerate(GP_CASES_LARGE):
+        X, n1, Xt, noise = gp_case(100 + i, M, D, N)
+        feats = torch.from_numpy(np.concatenate([X, Xt])).to(dev)
+        r = fit_gp_regions(feats, [np.arange(M)], [n1], [np.arange(M, M + N)], init_noise=[noise], return_float64=True)[0]
+        assert rel_err(r[5].cpu().numpy(), gold[f"c{i}_mu64"]) < TOL, (M, D)
+        assert rel_err(r[6].cpu().numpy(), gold[f"c{i}_var64"]) < TOL, (M, D)
+        assert np.allclose(r[0].cpu().numpy(), gold[f"c{i}_prob"], rtol=1e-6, atol=1e-7)
+        assert (r[2].cpu().numpy() == gold[f"c{i}_label"]).all()       # minimum posterior margin of these cases: 4e-3
+
+
 def test_gp_batching_and_chunking_do_not_change_results(dev, lib):
     idx = [0, 1, 2, 3, 4, 6]
     _, together = _fit_cases(dev, idx)

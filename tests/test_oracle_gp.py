@@ -51,6 +51,17 @@ def test_oracle_reproduces_golden(i):
     assert (r["label"] == gold[f"c{i}_label"]).all()
 
 
+def test_oracle_reproduces_large_golden_case():
+    """gp_cases_large.npz (M = 200 / 1000 / 520x32, used by the GPU suite) is oracle output: re-derive the first."""
+    from tests.golden.make_golden import GP_CASES_LARGE
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "gp_cases_large.npz"))
+    M, D, N = GP_CASES_LARGE[0]
+    X, n1, Xt, noise = gp_case(100, M, D, N)
+    r = G.fit_region_autograd(X, n1, Xt, noise)
+    assert rel_err(r["mu64"], gold["c0_mu64"]) < 1e-6 and rel_err(r["var64"], gold["c0_var64"]) < 1e-6
+    assert all(f"c{i}_mu64" in gold for i in range(len(GP_CASES_LARGE)))
+
+
 def test_degenerate_regions_are_finite():
     rng = np.random.default_rng(1)
     X = rng.normal(size=(2, 6)).astype(np.float32)                 # M = 1 + 1
