@@ -67,6 +67,7 @@ COLS = OrderedDict([
     ("regs", "launch__registers_per_thread"),
     ("dyn smem", "launch__shared_mem_per_block_dynamic"),
     ("warps active %", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+    ("DMMA pipe %", "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active"),
     ("FP64 pipe %", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
     ("SM throughput %", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("DRAM read", "dram__bytes_read.sum"),
