@@ -710,10 +710,11 @@ k_rl_panel(const Region* __restrict__ regs, const int2* __restrict__ ptiles, int
     }
 }
 
-// Trailing update with the block steps kb0 .. kb0+nk-1 (contraction over nk*64).  Updates are applied
-// two steps at a time: after an even step only the next block column / block row is brought up to date
-// (what the odd step's diag and panel need, nk = 1), after the odd step every remaining lower tile
-// receives both steps in one pass (nk = 2) - half the read-modify-write traffic of a per-step update.
+// Trailing update with the block steps kb0 .. kb0+nk-1 (contraction over nk*64).  Updates are applied a
+// group of steps at a time (ChunkTables::sweep_group): after any but the last step of a group only the next
+// block column / block row is brought up to date with the steps of the group so far (what the next diag and
+// panel need), after the last one every remaining lower tile receives the whole group in one pass - 1/group
+// of the read-modify-write traffic of a per-step update and a contraction long enough to fill the pipeline.
 __global__ void __launch_bounds__(GEMM_THREADS, 4)
 k_rl_update(const Region* __restrict__ regs, const int4* __restrict__ tiles, int kb0, int nk, GpParams prm,
             double* __restrict__ ws) {
@@ -1264,7 +1265,16 @@ struct ChunkTables {
     std::vector<int> cnt_gt;        // cnt_gt[kb] = #regions with nb > kb
     std::vector<int> panel_prefix;  // panel tiles of the first cnt_gt[kb] regions
     int nbmax;
+    int sweep_group;                // block steps whose trailing updates are applied in one pass
 };
+
+// Trailing updates of the sweep are applied `group` block steps at a time (contraction depth group * 64);
+// between two full passes only the next block column / block row is brought up to date.
+static int sweep_group_size() {
+    int g = 4;      // measured on the bench batch: 2 -> 1563 ms, 4 -> 1544 ms, 8 -> 1559 ms per step
+    if (const char* e = getenv("GAPRO_GP_SWEEP_GROUP")) g = atoi(e);
+    return g < 1 ? 1 : (g > 8 ? 8 : g);
+}
 
 
 // ---- opt-in per-phase profiling with CUDA events on the launching stream ------------------
@@ -1393,7 +1403,7 @@ struct Driver {
             }
             const int nu = tb.upd_off[kb + 1] - tb.upd_off[kb];
             if (nu > 0) {
-                const int kb0 = (kb & 1) ? kb - 1 : kb, nk = (kb & 1) ? 2 : 1;
+                const int kb0 = kb - kb % tb.sweep_group, nk = kb - kb0 + 1;
                 k_rl_update<<<nu, GEMM_THREADS, GEMM_SMEM, stream>>>(tb.regs, tb.upd + tb.upd_off[kb], kb0, nk, p, ws);
                 ++g_launches;
             }
@@ -1500,16 +1510,18 @@ int setup_chunk(std::vector<Region>& rs, char* aux, cudaStream_t stream, ChunkTa
     tb.rows = (int2*)put(rows.data(), rows.size() * 8);
     tb.rowsp = (int2*)put(rowsp.data(), rowsp.size() * 8);
     tb.panel = (int2*)put(panel.data(), panel.size() * 8);
-    // update tiles, step-major.  Even step kb: only block column kb+1 (K tiles) and block row kb+1
-    // (S tiles); odd step kb: every lower tile (i, j <= i) with i > kb, for both steps of the pair.
+    // update tiles, step-major.  Steps are grouped by sweep_group.  Last step of a group: every lower tile
+    // (i, j <= i) with i > kb receives all steps of the group in one pass; any other step kb: only block
+    // column kb+1 (K tiles) and block row kb+1 (S tiles) receive the steps of the group so far.
     std::vector<int4> upd;
+    tb.sweep_group = sweep_group_size();
     tb.upd_off.assign(tb.nbmax + 1, 0);
     for (int kb = 0; kb < tb.nbmax; ++kb) {
         tb.upd_off[kb] = (int)upd.size();
         const int live = tb.cnt_gt[kb];
         for (int r = 0; r < live; ++r) {
             const int nb = rs[r].nb;
-            if (kb & 1) {
+            if (kb % tb.sweep_group == tb.sweep_group - 1) {
                 for (int i = nb - 1; i > kb; --i)
                     for (int j = 0; j <= i; ++j) upd.push_back(make_int4(r, i, j, 0));
             } else if (kb + 1 < nb) {
