@@ -18,6 +18,9 @@ lives in `gpytorch` (version not pinned by the reference, restated at
 1.8.1-style constants), which is not installable here, and the reference ships
 no golden vectors for it.  That part is a restatement of
 `/root/reference/gapro/gaussian_process_utils.py` and of gpytorch's published
-algorithm, validated only against itself (autograd vs. hand-derived gradients,
-torch ops vs. explicit loops).
+algorithm, validated against itself (autograd vs. hand-derived gradients,
+torch ops vs. explicit loops) and against independently written textbook
+formulas of the same model (unwhitened SVGP predictive, dense-Gaussian KL,
+adaptive quadrature of the expected log-likelihood, torch.optim.Adam) in
+tests/test_oracle_gp.py - not against gpytorch's own float32 execution.
 """

@@ -107,3 +107,88 @@ def test_cholesky_adjoint_shortcut_used_by_the_cuda_path():
     S = -0.5 * (phi + phi.T)
     assert np.abs(S - it["symP"]).max() < 1e-14
     assert np.abs(it["Linv"].T @ S @ it["Linv"] - it["G_K"]).max() < 1e-13
+
+
+# ------------------------------------------------------------------------------------------------
+# model-level known answers: the restated forward / loss against textbook formulas written independently
+# (dense covariances, adaptive quadrature) - what gpytorch documents its whitened SVGP to compute
+# ------------------------------------------------------------------------------------------------
+def _random_state(M=6, N=5, D=3, seed=3):
+    rng = np.random.default_rng(seed)
+    Z = rng.normal(size=(M, D))
+    X = rng.normal(size=(N, D))
+    m = rng.normal(size=M) * 0.4
+    T = np.tril(rng.normal(size=(M, M)) * 0.3) + np.eye(M)
+    return rng, Z, X, m, T, 0.15, 0.4, -0.3
+
+
+def _dense_kernel(A, B, ell, s):
+    d2 = ((A[:, None, :] - B[None, :, :]) ** 2).sum(-1) / ell ** 2
+    return s * np.exp(-0.5 * d2)
+
+
+def test_whitened_posterior_equals_the_unwhitened_textbook_formulas():
+    """q(u) = N(L m, L T T^T L^T) with K_zz = L L^T:  mean = K_xz K_zz^-1 (L m) + c,
+    var = k_xx + j_x - diag(K_xz K_zz^-1 K_zx) + diag(K_xz K_zz^-1 S_u K_zz^-1 K_zx)."""
+    _, Z, X, m, T, c, rs, rl = _random_state()
+    ell, s = np.log1p(np.exp(rl)), np.log1p(np.exp(rs))
+    tp = [torch.tensor(a, dtype=torch.float64) for a in (Z, m, T, c, rs, rl)]
+    mu, var, _ = G._forward(tp, torch.tensor(X), 1e-4, 1e-4, "fp64")
+    Kzz = _dense_kernel(Z, Z, ell, s) + 1e-4 * np.eye(len(Z))
+    Kzx = _dense_kernel(Z, X, ell, s)
+    L = np.linalg.cholesky(Kzz)
+    Su = L @ T @ T.T @ L.T
+    W = np.linalg.solve(Kzz, Kzx)                       # K_zz^-1 K_zx
+    mean = W.T @ (L @ m) + c
+    v = s + 1e-4 - np.einsum("ij,ij->j", Kzx, W) + np.einsum("ij,ik,kj->j", W, Su, W)
+    assert np.allclose(mu.numpy(), mean, rtol=1e-10, atol=1e-12)
+    assert np.allclose(var.numpy(), np.maximum(v, 1e-6), rtol=1e-9, atol=1e-12)
+
+
+def test_kl_term_equals_the_dense_gaussian_kl():
+    """KL(N(m, T T^T) || N(0, I)) from the general formula with dense matrices."""
+    _, Z, X, m, T, c, rs, rl = _random_state(seed=5)
+    M = len(m)
+    S = T @ T.T
+    kl_dense = 0.5 * (np.trace(S) + m @ m - M - np.linalg.slogdet(S)[1])
+    y = np.ones(len(X))
+    tp = [torch.tensor(a, dtype=torch.float64) for a in (Z, m, T, c, rs, rl)]
+    loss = float(G._neg_elbo(tp, torch.tensor(X), torch.tensor(y), 1e-4, 1e-4, "fp64"))
+    mu, var, _ = G._forward(tp, torch.tensor(X), 1e-4, 1e-4, "fp64")
+    # expected log-likelihood by adaptive quadrature instead of 20-point Gauss-Hermite
+    from scipy import integrate, stats
+    ell_q = 0.0
+    for mu_i, v_i, y_i in zip(mu.numpy(), var.numpy(), y):
+        f = lambda t: stats.norm.logcdf(y_i * t) * stats.norm.pdf(t, loc=mu_i, scale=np.sqrt(v_i))
+        ell_q += integrate.quad(f, mu_i - 12 * np.sqrt(v_i), mu_i + 12 * np.sqrt(v_i), epsabs=1e-13, epsrel=1e-13)[0]
+    n = len(X)
+    assert abs(loss - (-(ell_q / n) + kl_dense / n)) < 1e-7
+
+
+def test_gauss_hermite_expectation_against_adaptive_quadrature():
+    """E_{f ~ N(mu, var)} log Phi(y f) with the 20 nodes at sqrt(2 var) t + mu and weights w / sqrt(pi)."""
+    from scipy import integrate, stats
+    t, w = np.polynomial.hermite.hermgauss(G.N_GH)
+    for mu, var, y in ((0.3, 0.5, 1.0), (-1.2, 2.0, -1.0), (2.5, 0.05, -1.0), (0.0, 1e-6, 1.0)):
+        gh = (w * stats.norm.logcdf(y * (np.sqrt(2 * var) * t + mu))).sum() / np.sqrt(np.pi)
+        f = lambda x: stats.norm.logcdf(y * x) * stats.norm.pdf(x, loc=mu, scale=np.sqrt(var))
+        sd = np.sqrt(var)
+        ref = integrate.quad(f, mu - 12 * sd, mu + 12 * sd, epsabs=1e-13, epsrel=1e-13)[0]
+        assert abs(gh - ref) < 2e-6 * max(1.0, abs(ref)), (mu, var, y, gh, ref)
+
+
+def test_adam_step_matches_torch_optim():
+    """oracle/_Adam (used by the manual fit and mirrored by the CUDA epilogues) against torch.optim.Adam."""
+    rng = np.random.default_rng(2)
+    p0 = [rng.normal(size=(4, 3)), rng.normal(size=5), np.array(0.3)]
+    grads = [[rng.normal(size=a.shape) for a in p0] for _ in range(4)]
+    opt = G._Adam([a.copy() for a in p0], 0.1)
+    tp = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in p0]
+    topt = torch.optim.Adam(tp, lr=0.1)
+    for g in grads:
+        opt.step([np.asarray(x) for x in g])
+        for t_, x in zip(tp, g):
+            t_.grad = torch.tensor(x, dtype=torch.float64)
+        topt.step()
+    for a, b in zip(opt.params, tp):
+        assert np.allclose(np.asarray(a), b.detach().numpy(), rtol=1e-12, atol=1e-14)
