@@ -37,6 +37,8 @@ from gapro_b200 import synthetic                       # noqa: E402
 from gapro_b200.gen_ps import synthetic_inputs         # noqa: E402
 from oracle import gp_oracle as G                      # noqa: E402
 
+MANY_BOXES = synthetic.SceneConfig(n_points=14_000, n_objects=34, s_target=600, overlap=0.5, n_nested=3)
+
 
 # ------------------------------------------------------------------------------------------------
 # stand-in for the absent torch_scatter extension (sequential, index order)
@@ -224,6 +226,17 @@ def main():
     out["deep_sem"], out["deep_inst"], out["deep_prob"] = sem.int().numpy(), inst.int().numpy(), prob.numpy()
     out["deep_mu"], out["deep_var"], out["deep_regions"] = mu.numpy(), var.numpy(), np.array(state["calls"])
     print(f"deep-feature scene: D={inp['mask_feats'].shape[1]}, {state['calls']} regions")
+    # --- more than 32 boxes (two 32-bit occupancy words on the device side), 41 GP regions, 7 nesting events;
+    # minimum posterior margin 1.5e-3, minimum gap of a contested merge 1.2e-2
+    inp = synthetic_inputs(synthetic.make_scene(23, MANY_BOXES))
+    T = as_ref_tensors(inp)
+    state["rng"], state["calls"] = np.random.default_rng(13), 0
+    sem, inst, prob, mu, var = R.gen_pseudo_label_gaussian_process(
+        T["xyz"], T["mask_feats"], T["spp"], T["instance_cls"], T["instance_box"], T["instance_box_volume"],
+        T["wall_box"], T["wall_volume"], thresh_spp_occu=0.999)
+    out["many_sem"], out["many_inst"], out["many_prob"] = sem.int().numpy(), inst.int().numpy(), prob.numpy()
+    out["many_mu"], out["many_var"], out["many_regions"] = mu.numpy(), var.numpy(), np.array(state["calls"])
+    print(f"many-box scene: {len(inp['instance_box']) + len(inp['wall_box']) + 1} boxes, {state['calls']} regions")
     # --- semantic confusion matrix (eval_ps_labels.py:152-172)
     cuda = torch.Tensor.cuda
     torch.Tensor.cuda = lambda self, *a, **k: self

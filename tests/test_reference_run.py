@@ -114,6 +114,21 @@ def test_oracle_equals_reference_run_on_deep_features(ref):
         assert np.array_equal(got, ref[f"deep_{key}"]), key
 
 
+def _many_box_inputs():
+    from tests.golden.make_ref_golden import MANY_BOXES
+    return synthetic_inputs(synthetic.make_scene(23, MANY_BOXES))
+
+
+def test_oracle_equals_reference_run_with_more_than_32_boxes(ref):
+    from oracle import gen_ps_oracle as O
+    inp = _many_box_inputs()
+    assert len(inp["instance_box"]) + len(inp["wall_box"]) + 1 > 32
+    res, dbg = O.gen_pseudo_label_oracle(*oracle_args(inp), thresh_spp_occu=0.999, noise_seed=13, return_debug=True)
+    assert len(dbg["regions"]) == int(ref["many_regions"]) > 30
+    for got, key in zip(res, ("sem", "inst", "prob", "mu", "var")):
+        assert np.array_equal(got, ref[f"many_{key}"]), key
+
+
 def test_confusion_matrix_equals_reference_run(ref):
     from gapro_b200.eval_ps_labels import get_scene_sem_conf
     conf = get_scene_sem_conf(torch.from_numpy(ref["conf_gt"]), torch.from_numpy(ref["conf_ps"]))
@@ -254,3 +269,10 @@ def test_cuda_cli_equals_reference_cli_run(dev, lib, ref, tmp_path, monkeypatch)
                 assert np.array_equal(a, want), (scan, key)
             else:
                 assert np.allclose(a, want, rtol=1e-4, atol=1e-7), (scan, key)
+
+
+@pytest.mark.gpu
+def test_cuda_equals_reference_run_with_more_than_32_boxes(dev, lib, ref):
+    """39 boxes (two occupancy words per superpoint), 41 GP regions, nesting events, contested merges: final labels
+    against the reference run (minimum posterior margin of the scene 1.5e-3, minimum merge gap 1.2e-2)."""
+    _check_cuda(_run_cuda(dev, _many_box_inputs(), 0.999, 13), ref, "many")
