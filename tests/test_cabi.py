@@ -89,6 +89,31 @@ def test_event_enumeration_equals_oracle_loop(lib, name, seed):
         assert (buf[q0:q1] == reg["inter"]).all()
 
 
+def test_event_enumeration_equals_oracle_loop_on_random_clutter(lib):
+    """25 small scenes with heavy overlap and nesting: the host state machine (gapro_enumerate_events) against the
+    oracle's pair loop, event for event (the oracle's loop is itself pinned to the reference's, test_reference_run.py)."""
+    fake = lambda X, n1, Xt, nz: dict(conf=np.full(len(Xt), .7, np.float32), label=np.ones(len(Xt), bool),
+                                      mu=np.zeros(len(Xt), np.float32), var=np.ones(len(Xt), np.float32))
+    cfg = synthetic.SceneConfig(n_points=1500, n_objects=12, s_target=120, overlap=0.7, n_nested=3)
+    kinds = {0: "nest", 1: "nest", 2: "gp"}
+    n_nest = n_gp = 0
+    for seed in range(200, 225):
+        inp = synthetic_inputs(synthetic.make_scene(seed, cfg))
+        _, dbg = O.gen_pseudo_label_oracle(*oracle_args(inp), thresh_spp_occu=0.999, fit_fn=fake, return_debug=True)
+        B = len(dbg["boxes"])
+        stride = 32 * ((B + 31) // 32)
+        excl, inter = counts_from_occupancy(dbg["occ_spp"], dbg["n_bbs"], stride)
+        ev = plan.enumerate_events(dbg["boxes"], excl, inter[None], np.array([0, B], np.int32), stride)
+        got = [(kinds[int(k)], int(a), int(b)) for k, a, b in zip(ev["ev_kind"], ev["ev_b1"], ev["ev_b2"])]
+        assert got == [(e[0], e[1], e[2]) for e in dbg["events"]], seed
+        for (k, a, b), e in zip(zip(ev["ev_kind"], ev["ev_b1"], ev["ev_b2"]), dbg["events"]):
+            if e[0] == "nest":
+                assert (a if k == _lib.EV_NEST_B1 else b) == e[3], seed
+        n_nest += sum(e[0] == "nest" for e in dbg["events"])
+        n_gp += sum(e[0] == "gp" for e in dbg["events"])
+    assert n_nest >= 10 and n_gp >= 50
+
+
 def test_event_enumeration_hand_cases(lib):
     # nested pair: b0 inside b1 -> NEST_B1 and break; b1 inside b0 -> NEST_B2
     small, big = [1, 1, 1.5, 2, 2, 2.5], [0, 0, 1, 4, 4, 3]
