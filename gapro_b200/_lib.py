@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgapro_b200.so")
 
 EV_NEST_B1, EV_NEST_B2, EV_GP = 0, 1, 2
-GP_NOT_PSD, GP_NAN = 1, 2
+GP_NOT_PSD, GP_NAN, GP_RETRY_SHIFT = 1, 2, 8
 
 _lib = None
 
@@ -50,12 +50,25 @@ _SIGNATURES = {
     "gapro_resolve_spp": (ctypes.c_int, [P, P, c_int32, P, P, P, P, P, c_int32, c_int32, P, P, P, P, P, P, P, P,
                                          P, P, P, P, P, P, P, P, P, P, P]),
     "gapro_broadcast_labels": (ctypes.c_int, [P, c_int64, P, P, P, P, P]),
+    "gapro_eval_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "gapro_eval_miou_scene": (ctypes.c_int, [P, P, P, P, c_int64, c_int32, c_int32, P, P, P, c_size_t, P]),
+    "gapro_eval_sem_conf": (ctypes.c_int, [P, P, c_int64, c_int32, P, P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
 
 class GaproError(RuntimeError):
     pass
+
+
+class GaproSceneError(GaproError):
+    """A GP region of one or more scenes could not be fitted (gpytorch would raise NotPSDError / NanError and
+    kill the run, gen_ps_utils.py:434-437).  `.scenes` maps the batch index of every failed scene to a message;
+    the other scenes of the batch were labelled and are in `.results` (None at the failed positions)."""
+
+    def __init__(self, scenes, results):
+        self.scenes, self.results = dict(scenes), results
+        super().__init__("; ".join(f"scene {i}: {m}" for i, m in sorted(self.scenes.items())))
 
 
 def load():

@@ -1344,6 +1344,36 @@ struct Driver {
     cudaStream_t s_hi = nullptr, s_lo = nullptr;
     cudaEvent_t ev_swept = nullptr, ev_stepped = nullptr;
     cudaEvent_t ev_prev_swept = nullptr;   // first sweep of the previous group: staggers the groups by one sweep
+    // careful mode (ONE region on the caller's stream, after the batched pass flagged it): every Cholesky is
+    // checked on the host and retried with psd_safe_cholesky's jitter ladder
+    bool careful = false;
+    int retries = 0;
+    bool failed = false;
+
+    // gpytorch.utils.cholesky.psd_safe_cholesky: plain attempt, then +1e-8 * 10^k on the diagonal for k = 0, 1, 2
+    // (float64 `cholesky_jitter`, max_tries 3), NotPSDError after that
+    int factor_careful(const GpParams& p) {
+        for (int level = 0;; ++level) {
+            GpParams q = p;
+            if (level) q.jitter_zz = p.jitter_zz + 1e-8 * pow(10.0, (double)(level - 1));
+            GAPRO_CUDA_TRY(cudaMemsetAsync(po.status + tb_orig, 0, 4, stream));
+            build(q);
+            cholesky(q);
+            int32_t h = 0;
+            GAPRO_CUDA_TRY(cudaMemcpyAsync(&h, po.status + tb_orig, 4, cudaMemcpyDeviceToHost, stream));
+            GAPRO_CUDA_TRY(cudaStreamSynchronize(stream));
+            if (!(h & GAPRO_GP_NOT_PSD)) {
+                retries += level;
+                return GAPRO_OK;
+            }
+            if (level == 3) {
+                retries += level;
+                failed = true;
+                return GAPRO_OK;
+            }
+        }
+    }
+    int tb_orig = 0;                       // careful mode: index of the region in the caller's order
 
     void to_hi() {
         if (!s_hi) return;
@@ -1434,8 +1464,13 @@ struct Driver {
     ++ph;
         to_hi();
         if (step == 1 && s_hi && ev_prev_swept) cudaStreamWaitEvent(s_hi, ev_prev_swept, 0);
-        PHASE(build(p))
-        PHASE(cholesky(p))
+        if (careful) {
+            if (failed || factor_careful(p) != GAPRO_OK || failed) return;
+            ph = 2;
+        } else {
+            PHASE(build(p))
+            PHASE(cholesky(p))
+        }
         to_lo();
         PHASE(gemm<PH_A>(tb.full, tb.n_full, p))
         PHASE(gemm<PH_B>(tb.full, tb.n_full, p))
@@ -1458,8 +1493,12 @@ struct Driver {
         const GpParams p = params(0, 1);
         prof_begin(PROF_PREDICT, stream);
         to_hi();
-        build(p);
-        cholesky(p);
+        if (careful) {
+            if (failed || factor_careful(p) != GAPRO_OK || failed) return;
+        } else {
+            build(p);
+            cholesky(p);
+        }
         to_lo();
         gemm<PH_A>(tb.wide, tb.n_wide, p);
         gemm<PH_B>(tb.wide, tb.n_wide, p);
@@ -1472,7 +1511,8 @@ struct Driver {
 };
 
 // lays out one chunk (regions already carry .base), uploads descriptors and tile tables
-int setup_chunk(std::vector<Region>& rs, char* aux, cudaStream_t stream, ChunkTables& tb) {
+int setup_chunk(std::vector<Region>& rs, char* aux, const char* aux_end, cudaStream_t stream, ChunkTables& tb,
+                size_t* consumed) {
     std::vector<int4> full, lower, wide;
     std::vector<int2> rows, rowsp, panel;
     tb.nbmax = 0;
@@ -1496,20 +1536,6 @@ int setup_chunk(std::vector<Region>& rs, char* aux, cudaStream_t stream, ChunkTa
     }
     // regions are sorted by nb descending, so {nb > kb} is the prefix of length cnt_gt[kb]
     for (int kb = 0; kb <= tb.nbmax; ++kb) tb.panel_prefix[kb] = panel_before[tb.cnt_gt[kb]];
-    size_t o = 0;
-    auto put = [&](const void* src, size_t bytes) -> char* {
-        char* dst = aux + o;
-        o += gapro_align_up(bytes ? bytes : 1, 256);
-        if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
-        return dst;
-    };
-    tb.regs = (Region*)put(rs.data(), rs.size() * sizeof(Region));
-    tb.full = (int4*)put(full.data(), full.size() * 16);
-    tb.lower = (int4*)put(lower.data(), lower.size() * 16);
-    tb.wide = (int4*)put(wide.data(), wide.size() * 16);
-    tb.rows = (int2*)put(rows.data(), rows.size() * 8);
-    tb.rowsp = (int2*)put(rowsp.data(), rowsp.size() * 8);
-    tb.panel = (int2*)put(panel.data(), panel.size() * 8);
     // update tiles, step-major.  Steps are grouped by sweep_group.  Last step of a group: every lower tile
     // (i, j <= i) with i > kb receives all steps of the group in one pass; any other step kb: only block
     // column kb+1 (K tiles) and block row kb+1 (S tiles) receive the steps of the group so far.
@@ -1531,7 +1557,35 @@ int setup_chunk(std::vector<Region>& rs, char* aux, cudaStream_t stream, ChunkTa
         }
     }
     tb.upd_off[tb.nbmax] = (int)upd.size();
+    // table bytes of this group before anything is copied: the chunk was sized with aux_bytes(chunk), which
+    // covers the tables of all its groups plus ONE alignment slack term
+    {
+        const size_t sizes[8] = {rs.size() * sizeof(Region), full.size() * 16, lower.size() * 16, wide.size() * 16,
+                                 rows.size() * 8, rowsp.size() * 8, panel.size() * 8, upd.size() * 16};
+        size_t need = 0;
+        for (size_t b : sizes) need += gapro_align_up(b ? b : 1, 256);
+        if (aux + need > aux_end) {
+            gapro_set_error("gapro_gp_fit_batch: tile tables (%zu bytes) overrun the workspace by %zu bytes", need,
+                            (size_t)(aux + need - aux_end));
+            return GAPRO_ERR_WORKSPACE;
+        }
+    }
+    size_t o = 0;
+    auto put = [&](const void* src, size_t bytes) -> char* {
+        char* dst = aux + o;
+        o += gapro_align_up(bytes ? bytes : 1, 256);
+        if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+        return dst;
+    };
+    tb.regs = (Region*)put(rs.data(), rs.size() * sizeof(Region));
+    tb.full = (int4*)put(full.data(), full.size() * 16);
+    tb.lower = (int4*)put(lower.data(), lower.size() * 16);
+    tb.wide = (int4*)put(wide.data(), wide.size() * 16);
+    tb.rows = (int2*)put(rows.data(), rows.size() * 8);
+    tb.rowsp = (int2*)put(rowsp.data(), rowsp.size() * 8);
+    tb.panel = (int2*)put(panel.data(), panel.size() * 8);
     tb.upd = (int4*)put(upd.data(), upd.size() * 16);
+    *consumed = o;
     tb.n_full = (int)full.size();
     tb.n_lower = (int)lower.size();
     tb.n_wide = (int)wide.size();
@@ -1598,9 +1652,17 @@ struct StreamPool {
     cudaEvent_t stepped[MAX_GROUPS] = {};
     bool ready = false;
 };
-thread_local StreamPool g_pool;
+// streams and events belong to the device that was current when they were created: one pool per device
+constexpr int MAX_DEVICES = 64;
+thread_local StreamPool g_pools[MAX_DEVICES];
+thread_local StreamPool* g_pool_ptr = &g_pools[0];
+#define g_pool (*g_pool_ptr)
 
 static int ensure_pool() {
+    int dev = 0;
+    GAPRO_CUDA_TRY(cudaGetDevice(&dev));
+    GAPRO_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "gp: device ordinal %d not supported", dev);
+    g_pool_ptr = &g_pools[dev];
     if (g_pool.ready) return GAPRO_OK;
     int least = 0, greatest = 0;
     GAPRO_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
@@ -1640,7 +1702,12 @@ static int allow_smem(K kernel, int bytes) {
 }
 
 static int set_kernel_attributes() {
-    static bool done = false;
+    // cudaFuncSetAttribute is per device (several engines may live in one process)
+    static bool done_dev[MAX_DEVICES] = {};
+    int dev = 0;
+    GAPRO_CUDA_TRY(cudaGetDevice(&dev));
+    GAPRO_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "gp: device ordinal %d not supported", dev);
+    bool& done = done_dev[dev];
     if (done) return GAPRO_OK;
     int rc = allow_smem(k_build, (TB * 64 + 2 * 64 * (TB + 1)) * 8);
     if (rc == GAPRO_OK) rc = allow_smem(k_rl_diag, DIAG_SMEM);
@@ -1673,7 +1740,7 @@ static int set_kernel_attributes() {
 static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& all, const int32_t* train_idx,
                        const int32_t* test_idx, const float* init_noise, int32_t iters, int32_t stop_phase, double lr,
                        double jitter_zz, double jitter_xx, PredictOut po, void* ws, size_t ws_bytes, bool do_predict,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, bool careful = false, int* retries_out = nullptr, bool* failed_out = nullptr) {
     GAPRO_REQUIRE(D >= 1 && D <= 64, "gp: feature dimension %d not in [1, 64]", D);
     int rc = set_kernel_attributes();
     if (rc != GAPRO_OK) return rc;
@@ -1698,7 +1765,7 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
                             all[pos].M, all[pos].N);
             return GAPRO_ERR_WORKSPACE;
         }
-        const int G = n_groups_for(chunk.size());
+        const int G = careful ? 1 : n_groups_for(chunk.size());
         if (G > 1 && (rc = ensure_pool()) != GAPRO_OK) return rc;
         // round-robin over the size-sorted list: every group sees the same size distribution
         std::vector<std::vector<Region>> groups(G);
@@ -1718,6 +1785,8 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
                 d.stream = d.s_hi;
                 if (g > 0 && !getenv("GAPRO_GP_NO_STAGGER")) d.ev_prev_swept = g_pool.swept[g - 1];
             }
+            d.careful = careful;
+            if (careful) d.tb_orig = groups[g][0].orig;
             d.D = D;
             d.lr = lr;
             d.jitter_zz = jitter_zz;
@@ -1725,9 +1794,10 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             d.ws = (double*)ws;
             d.n_regs = (int)groups[g].size();
             d.po = po;
-            rc = setup_chunk(groups[g], aux, stream, d.tb);     // uploads on the caller's stream, then syncs
+            size_t used = 0;
+            rc = setup_chunk(groups[g], aux, (const char*)ws + ws_bytes, stream, d.tb, &used);   // uploads, then syncs
             if (rc != GAPRO_OK) return rc;
-            aux += aux_bytes(groups[g]);
+            aux += used;
         }
         if (G > 1) {
             GAPRO_CUDA_TRY(cudaEventRecord(g_pool.fork, stream));
@@ -1764,6 +1834,10 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
                 GAPRO_CUDA_TRY(cudaStreamWaitEvent(stream, g_pool.join[g], 0));
             }
         GAPRO_KERNEL_CHECK();
+        if (careful) {
+            if (retries_out) *retries_out = drv[0].retries;
+            if (failed_out) *failed_out = drv[0].failed;
+        }
         pos += chunk.size();
         if (pos < all.size()) GAPRO_CUDA_TRY(cudaStreamSynchronize(stream));   // workspace is reused
     }
@@ -1792,8 +1866,33 @@ extern "C" int gapro_gp_fit_batch(const float* feats_spp, int32_t D, int32_t n_r
     GAPRO_CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)n_regions * 4, stream));
     std::vector<Region> all = sorted_regions(n_regions, train_off, n_b1, test_off);
     PredictOut po{out_prob, out_conf, out_mu, out_var, out_label, out_mu64, out_var64, status};
-    return run_regions(feats_spp, D, all, train_idx, test_idx, init_noise, iters, 0, lr, jitter_zz, jitter_xx, po, ws,
-                       ws_bytes, true, stream);
+    int rc = run_regions(feats_spp, D, all, train_idx, test_idx, init_noise, iters, 0, lr, jitter_zz, jitter_xx, po, ws,
+                         ws_bytes, true, stream);
+    if (rc != GAPRO_OK) return rc;
+    // The batched pass has no host round trip inside its 50 steps, so a non-positive pivot is only flagged there.
+    // Regions it flagged (none in practice at jitter 1e-4 in float64) are fitted again one at a time with the retry
+    // ladder of psd_safe_cholesky; status then carries the retry count, and GAPRO_GP_NOT_PSD only if the ladder
+    // was exhausted (where gpytorch raises NotPSDError).
+    std::vector<int32_t> h(n_regions);
+    GAPRO_CUDA_TRY(cudaMemcpyAsync(h.data(), status, (size_t)n_regions * 4, cudaMemcpyDeviceToHost, stream));
+    GAPRO_CUDA_TRY(cudaStreamSynchronize(stream));
+    for (const Region& r : all) {
+        if (!(h[r.orig] & GAPRO_GP_NOT_PSD)) continue;
+        std::vector<Region> one(1, r);
+        int retries = 0;
+        bool failed = false;
+        rc = run_regions(feats_spp, D, one, train_idx, test_idx, init_noise, iters, 0, lr, jitter_zz, jitter_xx, po, ws,
+                         ws_bytes, true, stream, true, &retries, &failed);
+        if (rc != GAPRO_OK) return rc;
+        int32_t w = 0;
+        GAPRO_CUDA_TRY(cudaMemcpyAsync(&w, status + r.orig, 4, cudaMemcpyDeviceToHost, stream));
+        GAPRO_CUDA_TRY(cudaStreamSynchronize(stream));
+        w = (w & GAPRO_GP_NAN) | (failed ? GAPRO_GP_NOT_PSD : 0) |
+            ((retries > 0xffff ? 0xffff : retries) << GAPRO_GP_RETRY_SHIFT);
+        GAPRO_CUDA_TRY(cudaMemcpyAsync(status + r.orig, &w, 4, cudaMemcpyHostToDevice, stream));
+        GAPRO_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return GAPRO_OK;
 }
 
 

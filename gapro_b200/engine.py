@@ -76,8 +76,15 @@ class GaproEngine:
     def _workspace(self, key: str, nbytes: int) -> torch.Tensor:
         buf = self._ws.get(key)
         if buf is None or buf.numel() < nbytes:
+            # drop EVERY reference to the old buffer before growing: old + new do not fit side by side
+            # when the GP workspace is most of the HBM
+            buf = None
             self._ws[key] = None
-            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            try:
+                buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            except torch.OutOfMemoryError:
+                torch.cuda.empty_cache()
+                buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
             self._ws[key] = buf
         return buf
 
@@ -87,7 +94,8 @@ class GaproEngine:
     # ------------------------------------------------------------------ main entry
     def run(self, scenes: Sequence[SceneInputs], instance_classes=18, ground_h=0.1, training_iter=50,
             thresh_spp_occu=0.8, jitter_zz=1e-4, jitter_xx=1e-4, lr=0.1, debug: bool = False,
-            want_cnt_in: bool = False, keep: bool = False, stages_only: bool = False):
+            want_cnt_in: bool = False, keep: bool = False, stages_only: bool = False, on_error: str = "raise",
+            plan_only: bool = False):
         """Returns a list of (sem[N] i32, inst[N] i32, prob[N] f32, mu[S] f32, var[S] f32) device
         tensors, one tuple per scene — the return of gen_pseudo_label_gaussian_process
         (/root/reference/gapro/gen_ps_utils.py:482) — plus a BatchDebug when debug=True."""
@@ -202,6 +210,15 @@ class GaproEngine:
         n_ev, R, gp_ev, inter_len = pl["n_events"], pl["n_regions"], pl["gp_ev"], pl["inter_len"]
         ev_list_off, n_inter_total, n_test_total = pl["ev_list_off"], pl["n_inter_total"], pl["n_test_total"]
         n_train_total, test_off, train_off, m1, m2 = pl["n_train_total"], pl["test_off"], pl["train_off"], pl["m1"], pl["m2"]
+        if plan_only:
+            # cost estimate for load balancing (sharding.py): what the cheap stages A / A' / P say about the GP work
+            # of every scene - sum of M^3 over its regions (the GP stage is ~385 * M^3 flops per region)
+            m = (m1 + m2).astype(np.float64)
+            rs = pl["region_scene"]
+            return dict(sum_m3=np.bincount(rs, weights=m ** 3, minlength=ns)[:ns] if R else np.zeros(ns),
+                        n_regions=np.bincount(rs, minlength=ns)[:ns] if R else np.zeros(ns, np.int64),
+                        max_m=np.array([m[rs == i].max() if np.any(rs == i) else 0 for i in range(ns)]),
+                        n_points=np.array(n_pts), n_spp=np.diff(spp_off).astype(np.int64))
         L_scene, L_b1, L_b2, L_off = pl["list_scene"], pl["list_b1"], pl["list_b2"], pl["list_off"]
         n_lists = len(L_scene)
         lists_idx = torch.empty(max(n_inter_total + n_train_total, 1), dtype=torch.int32, device=dev)
@@ -222,6 +239,8 @@ class GaproEngine:
         gp_var64 = torch.empty(max(n_test_total, 1), dtype=torch.float64, device=dev) if debug else None
         gp_launches = 0
         noise = None
+        failed_scenes = {}
+        gp_retries = np.zeros(0, np.int64)
         if R:
             noise = self._make_noise(scenes, ev_scene[gp_ev], m1 + m2, n_train_total)
             n_b1 = m1.astype(np.int32)
@@ -246,12 +265,14 @@ class GaproEngine:
             gp_launches = int(lib.gapro_gp_last_launch_count())
             n_launch += gp_launches
             st = status.cpu().numpy()
-            if np.any(st & _lib.GP_NOT_PSD):
-                bad = int(np.flatnonzero(st & _lib.GP_NOT_PSD)[0])
-                raise _lib.GaproError(f"NotPSDError: K_ZZ of GP region {bad} is not positive definite "
-                                      "(gpytorch's psd_safe_cholesky would raise here too)")
-            if np.any(st & _lib.GP_NAN):
-                raise _lib.GaproError("NanError: non-finite GP posterior")
+            gp_retries = (st >> _lib.GP_RETRY_SHIFT) & 0xffff
+            # a failed region fails ITS scene only (the reference would have died on that scene, gen_ps_utils.py:434-437)
+            for r in np.flatnonzero(st & (_lib.GP_NOT_PSD | _lib.GP_NAN)):
+                sc = int(ev_scene[gp_ev[r]])
+                what = ("NotPSDError: K_ZZ is not positive definite after the jitter retries of psd_safe_cholesky"
+                        if st[r] & _lib.GP_NOT_PSD else "NanError: non-finite GP posterior")
+                failed_scenes.setdefault(sc, f"GP region {int(r)} (boxes {int(ev_b1[gp_ev[r]])}, "
+                                             f"{int(ev_b2[gp_ev[r]])}, M={int(m1[r] + m2[r])}): {what}")
 
         # ---- S0 + M + D + labels, then E ------------------------------------------------------
         ev_gp_off = pl["ev_gp_off"]
@@ -288,12 +309,17 @@ class GaproEngine:
         out = []
         for i in range(ns):
             p0, p1, s0, s1 = int(pt_off[i]), int(pt_off[i + 1]), int(spp_off[i]), int(spp_off[i + 1])
-            out.append((sem[p0:p1], inst[p0:p1], prob[p0:p1], mu_spp[s0:s1], var_spp[s0:s1]))
-        self.last_stats = dict(n_points=N, n_spp=St, n_boxes=Bt, n_events=n_ev, n_regions=R,
+            out.append(None if i in failed_scenes else
+                       (sem[p0:p1], inst[p0:p1], prob[p0:p1], mu_spp[s0:s1], var_spp[s0:s1]))
+        self.last_errors = failed_scenes
+        self.last_stats = dict(gp_cholesky_retries=int(gp_retries.sum()),
+                               n_points=N, n_spp=St, n_boxes=Bt, n_events=n_ev, n_regions=R,
                                sum_m=n_train_total, sum_m3=float(((m1 + m2).astype(np.float64) ** 3).sum()) if R else 0.0,
                                launches=n_launch, gp_launches=gp_launches, feat_dim=D,
                                m_list=(m1 + m2).astype(np.int64) if R else np.zeros(0, np.int64),
                                n_list=inter_len[gp_ev] if R else np.zeros(0, np.int64))
+        if failed_scenes and on_error == "raise":
+            raise _lib.GaproSceneError(failed_scenes, out)
         if not debug:
             return out
         dbg = BatchDebug(spp_off=spp_off, box_off=box_off, boxes=boxes_h, boxes_vol=boxes_vol.cpu().numpy(),

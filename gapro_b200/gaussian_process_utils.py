@@ -76,8 +76,10 @@ def fit_gp_regions(feats_spp, train_lists, n_b1, test_lists, init_noise=None, tr
                                       mu.data_ptr(), var.data_ptr(), p(mu64), p(var64), status.data_ptr(),
                                       ws.data_ptr(), ws.numel(), stream), "gapro_gp_fit_batch")
     st = status.cpu().numpy()
+    fit_gp_regions.last_retries = ((st >> _lib.GP_RETRY_SHIFT) & 0xffff).astype(np.int64)   # psd_safe_cholesky retries
     if np.any(st & _lib.GP_NOT_PSD):
-        raise _lib.GaproError("NotPSDError: K_ZZ not positive definite in region %d" % int(np.flatnonzero(st & 1)[0]))
+        raise _lib.GaproError("NotPSDError: K_ZZ not positive definite after the jitter retries in region %d"
+                              % int(np.flatnonzero(st & 1)[0]))
     if np.any(st & _lib.GP_NAN):
         raise _lib.GaproError("NanError: non-finite GP posterior")
     out = []

@@ -123,6 +123,48 @@ def _dist_env():
     return rank, world, local
 
 
+def _load_batch(pool, chunk, args):
+    """Disk -> host for a batch on worker threads; a scene that cannot be loaded (missing file, no labelled
+    instance - SURVEY Q9, where the reference crashes) is reported and skipped, the rest of the batch goes on."""
+    futs = [pool.submit(load_scene, fn, scan, args.use_deepfeat, args.deepfeat_folder) for fn, scan in chunk]
+
+    def collect():
+        out = []
+        for (fn, scan), f in zip(chunk, futs):
+            try:
+                out.append((fn, scan, f.result(), None))
+            except Exception as e:      # noqa: BLE001 - reported per scene, never fatal for the other scenes
+                out.append((fn, scan, None, f"{type(e).__name__}: {e}"))
+        return out
+    return collect
+
+
+def estimate_costs(items, args, device, pool):
+    """Cheap pass over `items` (stages U, F, A, A', P — no GP): seconds-of-GPU estimate per scene for the
+    cost-balanced sharding (per-scene cost ~ sum of M^3 over its GP regions, orders of magnitude
+    apart between scenes)."""
+    from .engine import get_engine
+    from .sharding import scene_cost
+    eng = get_engine(device)
+    costs = {}
+    chunks = [items[i:i + args.batch_scenes] for i in range(0, len(items), args.batch_scenes)]
+    pending = _load_batch(pool, chunks[0], args) if chunks else None
+    for ci, chunk in enumerate(chunks):
+        loaded = pending()
+        pending = _load_batch(pool, chunks[ci + 1], args) if ci + 1 < len(chunks) else None
+        ok = [(scan, inp) for _, scan, inp, err in loaded if err is None]
+        for _, scan, _, err in loaded:
+            if err is not None:
+                costs[scan] = 0.0
+        if not ok:
+            continue
+        scenes = [to_scene_inputs(inp[0], device, pin=True) for _, inp in ok]
+        st = eng.run(scenes, thresh_spp_occu=0.999, plan_only=True)
+        for k, (scan, _) in enumerate(ok):
+            costs[scan] = scene_cost(st["sum_m3"][k], st["n_points"][k], st["n_regions"][k])
+    return costs
+
+
 def main(argv=None):
     parser = argparse.ArgumentParser("GaPro_GenPS")
     parser.add_argument("--save_folder", type=str, default=osp.join(DATA_ROOT, "gaussian_process_kl_pseudo_labels"))
@@ -135,6 +177,12 @@ def main(argv=None):
     parser.add_argument("--load_workers", type=int, default=8, help="host threads reading / preparing the next batch")
     parser.add_argument("--per_point_uncertainty", action="store_true",
                         help="save mu/var broadcast to points (what the ISBNet/SPFormer loaders index)")
+    parser.add_argument("--jitter_zz", type=float, default=1e-4,
+                        help="K_ZZ jitter of the variational strategy: 1e-4 is gpytorch >= 1.6 (float32 "
+                             "settings.variational_cholesky_jitter), 1e-3 the add_jitter() default of gpytorch <= 1.5; "
+                             "the reference does not pin a gpytorch version")
+    parser.add_argument("--balance", choices=["cost", "static"], default="cost",
+                        help="multi-GPU sharding: LPT by a cost estimated from the cheap stages, or round-robin")
     args = parser.parse_args(argv)
 
     rank, world, local = _dist_env()
@@ -145,36 +193,65 @@ def main(argv=None):
     device = torch.device("cuda", local)
     os.makedirs(args.save_folder, exist_ok=True)
 
-    filenames = sorted(glob(osp.join(DATA_ROOT, "train", "*_inst_nostuff.pth")))
-    todo = []
-    for fn in filenames:
-        scan = osp.basename(fn)[:12]
-        if not osp.exists(osp.join(args.save_folder, scan + ".pth")):   # resume rule, gen_ps.py:39-41
-            todo.append((fn, scan))
-    todo = shard_scenes(todo, rank, world)
+    # ONE view of the work list for every rank: rank 0 applies the resume rule (gen_ps.py:39-41) and broadcasts,
+    # so ranks that list the save folder at different moments cannot disagree about who owns which scene
+    todo = None
+    if rank == 0:
+        filenames = sorted(glob(osp.join(DATA_ROOT, "train", "*_inst_nostuff.pth")))
+        todo = [(fn, osp.basename(fn)[:12]) for fn in filenames
+                if not osp.exists(osp.join(args.save_folder, osp.basename(fn)[:12] + ".pth"))]
+    if world > 1:
+        box = [todo]
+        dist.broadcast_object_list(box, src=0)
+        todo = box[0]
+
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=max(1, min(args.load_workers, args.batch_scenes)))
+    t0 = time.time()
+    balance = None
+    if world > 1 and args.balance == "cost" and todo:
+        from .sharding import balance_stats, lpt_assignment
+        part = estimate_costs(todo[rank::world], args, device, pool)
+        merged = {}
+        for d in gather_records([part], world):
+            merged.update(d)
+        costs = [merged.get(scan, 0.0) for _, scan in todo]
+        assign = lpt_assignment(costs, world)
+        balance = balance_stats(costs, assign)
+        todo = [todo[i] for i in assign[rank]]          # heavy scenes first
+    else:
+        todo = shard_scenes(todo, rank, world)
 
     from .eval_ps_labels import get_miou_scene
     ious, meta = [], []
-    t0 = time.time()
     chunks = [todo[i:i + args.batch_scenes] for i in range(0, len(todo), args.batch_scenes)]
     # host side of the NEXT batch (disk reads, alignment, boxes) runs on worker threads while the GPU
     # works on the current one
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=max(1, min(args.load_workers, args.batch_scenes)))
-    submit = lambda chunk: [pool.submit(load_scene, fn, scan, args.use_deepfeat, args.deepfeat_folder)
-                            for fn, scan in chunk]
-    pending = submit(chunks[0]) if chunks else []
+    pending = _load_batch(pool, chunks[0], args) if chunks else None
     for ci, chunk in enumerate(chunks):
-        loaded = [f.result() for f in pending]
-        pending = submit(chunks[ci + 1]) if ci + 1 < len(chunks) else []
-        scenes, gts = [], []
-        for (fn, scan), (inp, sem, inst) in zip(chunk, loaded):
+        loaded = pending()
+        pending = _load_batch(pool, chunks[ci + 1], args) if ci + 1 < len(chunks) else None
+        scenes, kept = [], []
+        for fn, scan, res, err in loaded:
+            if err is not None:
+                print(f"[rank {rank}] {scan}: not labelled - {err}", flush=True)
+                meta.append((scan, 0, 0, err))
+                continue
+            inp, sem, inst = res
             seed = None if args.seed is None else (zlib.crc32(scan.encode()) ^ args.seed) & 0x7fffffff
             scenes.append(to_scene_inputs(inp, device, noise_seed=seed, pin=True))
-            gts.append((sem, inst))
+            kept.append((scan, sem, inst))
+        if not scenes:
+            continue
         results = gen_pseudo_labels_batch(scenes, instance_classes=18, ground_h=0.1, training_iter=50,
-                                          thresh_spp_occu=0.999, device=device)    # gen_ps.py:106-110
-        for (fn, scan), res, sc, (sem, inst) in zip(chunk, results, scenes, gts):
+                                          thresh_spp_occu=0.999, jitter_zz=args.jitter_zz, device=device,
+                                          on_error="mark")                          # gen_ps.py:106-110
+        errors = results.errors
+        for k, ((scan, sem, inst), res, sc) in enumerate(zip(kept, results, scenes)):
+            if res is None:      # a GP region of this scene failed: the scene is reported, the others are saved
+                print(f"[rank {rank}] {scan}: not labelled - {errors.get(k)}", flush=True)
+                meta.append((scan, 0, 0, errors.get(k)))
+                continue
             if args.eval_pslabel:      # gen_ps.py:116-124
                 s = torch.from_numpy(np.asarray(sem)).to(device).int()
                 g = torch.from_numpy(np.asarray(inst)).to(device).int()
@@ -185,22 +262,25 @@ def main(argv=None):
                 ious.append(iou)
             dense = torch.unique(sc.spp, return_inverse=True)[1] if args.per_point_uncertainty else None
             save_pseudo_labels(osp.join(args.save_folder, scan + ".pth"), res, args.per_point_uncertainty, dense)
-            meta.append((scan, int(res[0].numel()), int(res[3].numel())))
+            meta.append((scan, int(res[0].numel()), int(res[3].numel()), None))
+    t_rank = time.time() - t0
     if args.eval_pslabel:
         local_iou = torch.cat(ious) if ious else torch.zeros(0, device=device)
         if world > 1:
-            import torch.distributed as dist
             gathered = [None] * world
             dist.all_gather_object(gathered, local_iou.cpu())
             local_iou = torch.cat(gathered)
         if rank == 0 and local_iou.numel():
             print("Mean instance iou of pseudo labels", torch.mean(local_iou.float()).item())
     if world > 1:
-        import torch.distributed as dist
-        records = gather_records(meta, world)       # the one collective: label metadata
+        records = gather_records(meta, world)       # the one collective of the labelling pass: label metadata
+        walls = gather_records([t_rank], world)
         if rank == 0:
-            print(f"{len(records)} scenes / {sum(m[1] for m in records)} points labelled on {world} GPUs "
-                  f"in {time.time() - t0:.1f}s")
+            failed = [m for m in records if m[3] is not None]
+            print(f"{len(records) - len(failed)} scenes / {sum(m[1] for m in records)} points labelled on {world} GPUs "
+                  f"in {time.time() - t0:.1f}s; per-rank wall max/mean {max(walls) / (sum(walls) / world):.3f}"
+                  + (f"; estimated load max/mean {balance['max_over_mean']:.3f}" if balance else "")
+                  + (f"; {len(failed)} scenes FAILED: {[m[0] for m in failed]}" if failed else ""))
         dist.destroy_process_group()
     if rank == 0:
         print("Finish")

@@ -55,13 +55,27 @@ def gen_pseudo_label_gaussian_process(
     return res[0]
 
 
+class BatchResults(list):
+    """One 5-tuple per scene; with on_error="mark" a scene whose GP fit failed holds None and `.errors` maps its
+    batch index to the message."""
+    errors: dict = {}
+
+
 def gen_pseudo_labels_batch(scenes, instance_classes=18, ground_h=0.1, training_iter=50, thresh_spp_occu=0.8,
-                            jitter_zz=1e-4, device=None, return_debug=False):
+                            jitter_zz=1e-4, device=None, return_debug=False, on_error="raise"):
     """Many scenes through ONE pass of the hot path (scenes are independent: gen_ps.py:36).
-    `scenes` is a sequence of SceneInputs; returns one 5-tuple per scene."""
+    `scenes` is a sequence of SceneInputs; returns one 5-tuple per scene.  A GP region that cannot be fitted
+    (NotPSDError after the jitter retries / NanError — where the reference dies, gen_ps_utils.py:434-437) fails
+    its own scene only: on_error="raise" raises GaproSceneError carrying the other scenes' results,
+    on_error="mark" returns None at that position."""
     eng = get_engine(device)
-    return eng.run(list(scenes), instance_classes=instance_classes, ground_h=ground_h, training_iter=training_iter,
-                   thresh_spp_occu=thresh_spp_occu, jitter_zz=jitter_zz, debug=return_debug)
+    res = eng.run(list(scenes), instance_classes=instance_classes, ground_h=ground_h, training_iter=training_iter,
+                  thresh_spp_occu=thresh_spp_occu, jitter_zz=jitter_zz, debug=return_debug, on_error=on_error)
+    if return_debug:
+        return res
+    out = BatchResults(res)
+    out.errors = dict(eng.last_errors)
+    return out
 
 
 def gen_pseudo_label_box2mask(coords_float, spp, instance_cls, instance_box, instance_box_volume,

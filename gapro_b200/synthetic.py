@@ -29,13 +29,19 @@ class SceneConfig:
     size_range: tuple = (0.3, 2.0)
     inst_id_gaps: bool = True
     shuffle: bool = True
+    n_giants: int = 0              # elevated multi-layer structures overlapping pairwise (the 8k-row regions of C4)
+    giant_layers: int = 6
+    max_height: float | None = None   # cap on the regular objects' height (keeps them below the giants)
 
 
 # named configurations of BASELINE.json:configs
 CONFIGS = {
     "c1": SceneConfig(),
     "c1_deep": SceneConfig(feat_dim=32),
-    "c4": SceneConfig(n_objects=80, s_target=12_000, n_nested=20, overlap=0.6, n_points=300_000),
+    # heavy-overlap stress (BASELINE configs[3]): 80 boxes = 58 overlapping + 20 nested + 2 elevated shelf
+    # structures whose pair is ONE region of ~8k superpoints (M >= 4096 training rows + the overlap zone)
+    "c4": SceneConfig(n_objects=78, s_target=17_500, n_nested=20, overlap=0.6, n_points=400_000, n_giants=2,
+                      max_height=1.0, size_range=(0.3, 1.4)),
     "c5": SceneConfig(n_points=1_000_000, n_objects=120, s_target=30_000, overlap=0.5,
                       room=((14.0, 20.0), (10.0, 16.0), (2.8, 3.4))),
     "tiny": SceneConfig(n_points=6_000, n_objects=6, s_target=300, overlap=0.5, n_nested=1),
@@ -73,6 +79,8 @@ def _place_objects(rng, cfg, room):
     for k in range(n_plain):
         size = rng.uniform(lo_s, hi_s, 3)
         size[2] = min(size[2], rz - 0.3)
+        if cfg.max_height is not None:
+            size[2] = min(size[2], cfg.max_height)
         if boxes and rng.random() < cfg.overlap:
             # push into a neighbour: overlap 10-50 % of the smaller extent along one axis
             nb = boxes[int(rng.integers(len(boxes)))]
@@ -157,6 +165,25 @@ def make_scene(seed: int, cfg: SceneConfig | str = "c1") -> Scene:
             (np.array([hi[0], lo[1], lo[2]]), np.array([0, e[1], 0]), np.array([0, 0, e[2]])),
         ]
         owner += [k] * 5
+    # giants: shelf-like structures above the regular objects, horizontal layers + 4 sides, consecutive ones
+    # overlapping by ~0.2 of the room length (IoU < 0.6, not nested): their pair is one very large GP region
+    for gi in range(cfg.n_giants):
+        w = 0.55 if cfg.n_giants > 1 else 0.8
+        x0 = 0.05 * rx + (0.9 - w) * rx * (gi / max(cfg.n_giants - 1, 1))
+        lo = np.array([x0, 0.35, 1.25])
+        hi = np.array([x0 + w * rx, ry - 0.35, min(rz - 0.15, 2.45)])
+        e = hi - lo
+        for z in np.linspace(lo[2], hi[2], cfg.giant_layers):
+            surfaces.append((np.array([lo[0], lo[1], z]), np.array([e[0], 0, 0]), np.array([0, e[1], 0])))
+        surfaces += [
+            (np.array([lo[0], lo[1], lo[2]]), np.array([e[0], 0, 0]), np.array([0, 0, e[2]])),
+            (np.array([lo[0], hi[1], lo[2]]), np.array([e[0], 0, 0]), np.array([0, 0, e[2]])),
+            (np.array([lo[0], lo[1], lo[2]]), np.array([0, e[1], 0]), np.array([0, 0, e[2]])),
+            (np.array([hi[0], lo[1], lo[2]]), np.array([0, e[1], 0]), np.array([0, 0, e[2]])),
+        ]
+        owner += [K + gi] * (cfg.giant_layers + 4)
+    n_reg = K
+    K = K + cfg.n_giants
     owner = np.array(owner)
     total_area = sum(np.linalg.norm(np.cross(u, v)) for _, u, v in surfaces)
     cell = float(np.sqrt(total_area / cfg.s_target))
@@ -165,7 +192,7 @@ def make_scene(seed: int, cfg: SceneConfig | str = "c1") -> Scene:
     inst = owner[face].astype(np.int64)
 
     # every object must own at least a few points (boxes come from points)
-    for k in range(K):
+    for k in range(n_reg):
         if not np.any(inst == k):
             j = int(rng.integers(len(pts)))
             f = 5 + 5 * k

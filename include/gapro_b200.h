@@ -54,6 +54,10 @@ extern "C" {
 /* per-region status bits written by gapro_gp_fit_batch */
 #define GAPRO_GP_NOT_PSD 1 /* non-positive Cholesky pivot (gpytorch would raise NotPSDError) */
 #define GAPRO_GP_NAN 2     /* non-finite posterior                                           */
+/* bits 8..23: how many Cholesky attempts needed extra diagonal jitter (+1e-8 * 10^k, k < 3) - the retry ladder of
+ * gpytorch's psd_safe_cholesky behind gaussian_process_utils.py:417; GAPRO_GP_NOT_PSD is set only when the ladder
+ * was exhausted, which is where gpytorch raises NotPSDError */
+#define GAPRO_GP_RETRY_SHIFT 8
 
 int gapro_version(void);
 const char* gapro_last_error(void);
@@ -289,6 +293,22 @@ int gapro_resolve_spp(const uint32_t* occ_bits, const int32_t* n_bbs, int32_t wo
  */
 int gapro_broadcast_labels(const int32_t* spp_gid, int64_t n_points, const void* packed_spp, int32_t* sem,
                            int32_t* inst, float* prob, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Ev — pseudo-label quality (`--eval_pslabel`, gen_ps.py:116-124).  Replaces
+ * get_miou_scene (eval_ps_labels.py:100-147): for every ground-truth instance id g in [0, n_gt) the best IoU
+ * with a pseudo instance of the same class (class of an instance = semantic label of its first point; IoU in
+ * float32 with the 1e-4 of cal_iou, :36-43).  One pass over the points fills the (n_gt+1) x (n_ps+1)
+ * contingency table with integer atomics; max_iou[g] float, valid[g] = 1 when id g is in use and its class
+ * is >= 0 (the rows the reference keeps, :139).  All label arrays dev int32[n_points]; n_gt / n_ps = max id + 1.
+ */
+size_t gapro_eval_workspace_bytes(int32_t n_gt, int32_t n_ps);
+int gapro_eval_miou_scene(const int32_t* gt_sem, const int32_t* gt_inst, const int32_t* ps_sem, const int32_t* ps_inst,
+                          int64_t n_points, int32_t n_gt, int32_t n_ps, float* max_iou, int32_t* valid, void* ws,
+                          size_t ws_bytes, void* stream);
+/* get_scene_sem_conf (eval_ps_labels.py:152-172): conf dev int64[num_classes^2], row = ground truth */
+int gapro_eval_sem_conf(const int32_t* gt_sem, const int32_t* ps_sem, int64_t n_points, int32_t num_classes,
+                        int64_t* conf, void* stream);
 
 #ifdef __cplusplus
 }

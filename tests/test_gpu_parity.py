@@ -490,3 +490,138 @@ def test_extension_is_the_code_that_ran(engine):
     assert engine.last_stats["launches"] > 100 and engine.last_stats["gp_launches"] > 50
     loaded = open("/proc/self/maps").read()
     assert "libgapro_b200.so" in loaded
+
+
+# ------------------------------------------------------------------- BASELINE.json sizes (round 2)
+def test_gp_region_of_8k_superpoints_matches_golden(dev, lib):
+    """configs[3]: M = 4200 training rows + 3800 test rows (66 blocks of 64, ~2 GB of region state) against the
+    committed fp64-oracle vectors (tests/golden/make_golden_fullsize.py)."""
+    from gapro_b200.gaussian_process_utils import fit_gp_regions
+    from tests.golden.make_golden_fullsize import GP_8K
+    gold = np.load(os.path.join(GOLD_DIR, "gp_case_8k.npz"))
+    i, M, D, N = GP_8K
+    X, n1, Xt, noise = gp_case(i, M, D, N)
+    feats = torch.from_numpy(np.concatenate([X, Xt])).to(dev)
+    r = fit_gp_regions(feats, [np.arange(M)], [n1], [np.arange(M, M + N)], init_noise=[noise], return_float64=True)[0]
+    assert rel_err(r[5].cpu().numpy(), gold["mu64"]) < TOL
+    assert rel_err(r[6].cpu().numpy(), gold["var64"]) < TOL
+    sure = np.abs(gold["prob"] - 0.5) > EPS
+    assert (r[2].cpu().numpy()[sure] == gold["label"][sure]).all()
+    assert np.allclose(r[0].cpu().numpy(), gold["prob"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["c1", "c3"])
+def test_full_size_scene_matches_offline_oracle_fixture(engine, dev, tag):
+    """One whole configs[1] scene (150k points, 93 GP regions) and scene 0 of the configs[2] bench batch (212k
+    points, regions up to M = 1126): labels bit-exact, mu / var 1e-4 (asserted 1e-5) against the fp64 oracle."""
+    from tests.golden.make_golden_fullsize import SCENES, input_digest, scene_args
+    gold = np.load(os.path.join(GOLD_DIR, f"scene_{tag}_full.npz"))
+    cfg_name, seed, nseed = SCENES[tag]
+    args = scene_args(cfg_name, seed)
+    assert input_digest(args) == str(gold["digest"])        # same synthetic inputs as the fixture was made from
+    from gapro_b200.engine import SceneInputs
+    T = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+    sc = SceneInputs(T(args[0], torch.float64), T(args[1], torch.float32), T(args[2], torch.int64), T(args[3], torch.int64),
+                     T(args[4], torch.float32), T(args[5], torch.float32),
+                     T(args[6], torch.float32) if len(args[6]) else [], T(args[7], torch.float32) if len(args[7]) else [],
+                     noise_seed=nseed)
+    out, dbg = engine.run([sc], thresh_spp_occu=0.999, debug=True)
+    assert len(dbg.regions) == int(gold["n_regions"])
+    B = dbg.box_off[1]
+    assert (np.packbits(unpack_bits(dbg.occ_bits, B), axis=1) == gold["occ_spp"]).all()
+    ref = [gold["sem"].astype(np.int32), gold["inst"].astype(np.int32), gold["prob"], gold["mu"], gold["var"]]
+    _compare_scene(out[0], ref, float(gold["min_margin"]))
+
+
+@pytest.mark.parametrize("name", ["c4", "c5"])
+def test_stress_configs_stages_bit_exact(engine, dev, name):
+    """configs[3] (80 boxes, a region of > 5k + 2.7k superpoints) and configs[4] (1M points, 125 boxes): four
+    occupancy words per superpoint; stages U, F, A, A', B, P and the region index lists bit-exact against the
+    oracle.  The GP runs with training_iter = 0 (prediction only) - its arithmetic at these sizes is covered by
+    the 8k-region golden test."""
+    from oracle import gen_ps_oracle as O
+    inp = synthetic_inputs(synthetic.make_scene(1000, name))
+    _, od = O.gen_pseudo_label_oracle(*oracle_args(inp), thresh_spp_occu=0.999, fit_fn=fake_fit, noise_seed=3,
+                                      return_debug=True)
+    outs, dbg = engine.run([to_scene_inputs(inp, dev, noise_seed=3)], thresh_spp_occu=0.999, training_iter=0, debug=True,
+                           want_cnt_in=True)
+    B = dbg.box_off[1]
+    assert dbg.occ_bits.shape[1] == 4 and B == len(od["boxes"])
+    assert (dbg.spp_gid.cpu().numpy() == od["spp_dense"]).all()
+    assert (dbg.boxes == od["boxes"]).all() and (dbg.boxes_vol == od["boxes_vol"]).all()
+    assert (dbg.cnt_in.cpu().numpy()[:, :B] == od["cnt_in"]).all()
+    assert (unpack_bits(dbg.occ_bits, B) == od["occ_spp"]).all()
+    assert (dbg.n_bbs.cpu().numpy() == od["n_bbs"]).all()
+    assert (dbg.feats_spp.cpu().numpy().view(np.uint32) == od["feats_spp"].view(np.uint32)).all()
+    kinds = {0: "nest", 1: "nest", 2: "gp"}
+    assert [(kinds[k], a, b) for k, a, b in dbg.events[0]] == [(e[0], e[1], e[2]) for e in od["events"]]
+    assert len(dbg.regions) == len(od["regions"])
+    big = 0
+    for r, o in zip(dbg.regions, od["regions"]):
+        assert (r["train_idx"] == np.concatenate([o["b1_inds"], o["b2_inds"]])).all()
+        assert (r["test_idx"] == o["inter"]).all()
+        big = max(big, len(r["train_idx"]) + len(r["test_idx"]))
+    assert big >= (7000 if name == "c4" else 3000)
+    sem, inst, prob, mu, var = [t.cpu().numpy() for t in outs[0]]
+    assert len(sem) == len(inp["xyz"]) and np.isfinite(mu).all() and ((prob >= 0.5) & (prob <= 1)).all()
+
+
+def test_cholesky_retry_ladder_and_failure_isolation(engine, dev, lib):
+    """psd_safe_cholesky behind gaussian_process_utils.py:417: a K_ZZ that is not positive definite is retried with
+    +1e-8 * 10^k on the diagonal (k < 3) before NotPSDError.  Duplicated rows at jitter_zz = -1e-9 make the Schur
+    complement of the duplicates ~ -2e-9 I (fails), +1e-8 repairs it: the region must come back fitted with a
+    retry count; jitter_zz = -2 can never be repaired and must
+    fail - and then only the scene that owns the region, not the batch."""
+    from gapro_b200.gaussian_process_utils import fit_gp_regions
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(4, 6)).astype(np.float32)
+    Xd = np.concatenate([X, X]).astype(np.float32)
+    feats = torch.from_numpy(np.concatenate([Xd, X[:2] * 0.5])).to(dev)
+    nz = rng.standard_normal(8).astype(np.float32)
+    ok = fit_gp_regions(feats, [np.arange(8)], [4], [np.array([8, 9])], init_noise=[nz], jitter_zz=1e-4)
+    assert fit_gp_regions.last_retries.sum() == 0
+    res = fit_gp_regions(feats, [np.arange(8)], [4], [np.array([8, 9])], init_noise=[nz], jitter_zz=-1e-9,
+                         training_iter=3)
+    assert fit_gp_regions.last_retries[0] >= 1
+    assert all(torch.isfinite(t.float()).all() for t in res[0])
+    with pytest.raises(_lib.GaproError, match="NotPSDError"):
+        fit_gp_regions(feats, [np.arange(8)], [4], [np.array([8, 9])], init_noise=[nz], jitter_zz=-2.0)
+    # and the healthy call after a failed one is unaffected
+    again = fit_gp_regions(feats, [np.arange(8)], [4], [np.array([8, 9])], init_noise=[nz], jitter_zz=1e-4)
+    assert all(torch.equal(a, b) for a, b in zip(ok[0], again[0]))
+    # scene isolation: scene 1 of a three-scene batch is given a jitter that cannot work through a monkeypatched
+    # per-scene... the engine has one jitter per batch, so poison ONE scene's features with NaN instead
+    inps = [synthetic_inputs(synthetic.make_scene(50 + i, "tiny")) for i in range(3)]
+    scenes = [to_scene_inputs(inp, dev, noise_seed=i) for i, inp in enumerate(inps)]
+    good = engine.run(scenes, thresh_spp_occu=0.999)
+    scenes[1].mask_feats = scenes[1].mask_feats.clone()
+    scenes[1].mask_feats[:] = float("nan")
+    with pytest.raises(_lib.GaproSceneError) as ei:
+        engine.run(scenes, thresh_spp_occu=0.999)
+    assert list(ei.value.scenes) == [1] and ei.value.results[1] is None
+    marked = engine.run(scenes, thresh_spp_occu=0.999, on_error="mark")
+    assert marked[1] is None and list(engine.last_errors) == [1]
+    for i in (0, 2):
+        for a, b in zip(good[i], marked[i]):
+            assert torch.equal(a, b)
+
+
+def test_eval_kernels_match_reference_run(dev, lib):
+    """SURVEY 8f rank 2 on the device: gapro_eval_miou_scene / gapro_eval_sem_conf against values the reference's
+    own eval_ps_labels.py produced (tests/golden/ref_outputs.npz) and against the host bincount path."""
+    from gapro_b200.eval_ps_labels import get_miou_scene, get_scene_sem_conf
+    ref = np.load(os.path.join(GOLD_DIR, "ref_outputs.npz"))
+    for name, seed in (("tiny", 3), ("small", 4)):
+        scene = synthetic.make_scene(seed, name)
+        sem_gt = torch.from_numpy(scene.sem.copy()).int()
+        inst_gt = torch.from_numpy(scene.inst.copy()).int()
+        sem_gt[sem_gt != -100] -= 2                                   # gen_ps.py:118-120
+        sem_gt[(sem_gt == -1) | (sem_gt == -2)] = 18
+        ps_sem = torch.from_numpy(ref[f"{name}_gp_sem"]).long()
+        ps_inst = torch.from_numpy(ref[f"{name}_gp_inst"]).long()
+        host = get_miou_scene(sem_gt.long(), inst_gt.long(), ps_sem, ps_inst)
+        got = get_miou_scene(sem_gt.long().to(dev), inst_gt.long().to(dev), ps_sem.to(dev), ps_inst.to(dev))
+        assert got.is_cuda and torch.equal(got.cpu(), host)                         # same float32 bits
+        assert np.allclose(got.cpu().numpy(), ref[f"{name}_miou"], rtol=0, atol=1e-6)
+    conf = get_scene_sem_conf(torch.from_numpy(ref["conf_gt"]).to(dev), torch.from_numpy(ref["conf_ps"]).to(dev))
+    assert conf.is_cuda and np.array_equal(conf.cpu().numpy(), ref["conf_matrix"])
