@@ -30,22 +30,41 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "scenes/sec pseudo-labelled"
-WORKLOAD = "c3: ScanNetv2-train-shaped synthetic scenes (N~U(50k,250k) pts, 12-40 boxes + 4 walls + floor, D=6), %d scenes/GPU/step"
+WORKLOADS = {
+    "c3": "c3: ScanNetv2-train-shaped synthetic scenes (scene i of the 1201-scene list: N~U(50k,250k) pts, 12-40 boxes + 4 walls + floor, D=6)",
+    "c1": "c1: ScanNet-shaped synthetic scenes (150k pts, 30 boxes + 4 walls + floor, ~4.7k superpoints, D=6)",
+    "c1_deep": "c1_deep: c1 with 32-d deep features (--use_deepfeat)",
+    "c4": "c4: heavy-overlap stress (400k pts, 80 boxes incl. 20 nested and two structures whose pair is one region of ~8k superpoints, M > 5k)",
+    "c5": "c5: S3DIS-area-shaped large rooms (1M pts, 120 boxes + 4 walls + floor, ~34k superpoints, regions up to M ~ 3.6k)",
+    "small": "small: 20k-point test scenes", "tiny": "tiny: 6k-point test scenes",
+}
 
 
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def make_inputs(rank, n_scenes, workload):
+def scene_ids(args, world):
+    """Scene indices of the job.  strong: the first --total-scenes scenes of the workload's list, whatever N is
+    (BASELINE configs[2]: a fixed scene list sharded over 1/2/4/8 GPUs).  weak: --scenes per GPU (round-1 shape)."""
+    n = args.total_scenes if args.mode == "strong" else args.scenes * world
+    return list(range(n))
+
+
+def make_input(idx, workload):
     from gapro_b200 import synthetic
     from gapro_b200.gen_ps import synthetic_inputs
-    inps = []
-    for i in range(n_scenes):
-        idx = rank * n_scenes + i
-        cfg = synthetic.c3_config(idx) if workload == "c3" else synthetic.CONFIGS[workload]
-        inps.append(synthetic_inputs(synthetic.make_scene(1000 + idx, cfg), use_deepfeat=cfg.feat_dim == 32))
-    return inps
+    cfg = synthetic.c3_config(idx) if workload == "c3" else synthetic.CONFIGS[workload]
+    return synthetic_inputs(synthetic.make_scene(1000 + idx, cfg), use_deepfeat=cfg.feat_dim == 32)
+
+
+def static_config(args, world):
+    """The part of `config` both arms share word for word (the driver compares the two lines' configs)."""
+    ids = scene_ids(args, world)
+    return {"workload": WORKLOADS[args.workload], "mode": args.mode, "total_scenes": len(ids),
+            "scenes_per_pass": args.scenes, "gp_iters": 50, "thresh_spp_occu": 0.999,
+            "sharding": "LPT by the cost the cheap stages A/A'/P estimate (sum M^3 per scene)" if world > 1 else "single GPU",
+            "l2": "256 MiB buffer written between passes (flush)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -78,10 +97,17 @@ def _fit_one(job):
     return time.perf_counter() - t0
 
 
-def cpu_scene_time(inp, budget_s, pool, n_workers):
-    """Wall-clock seconds the CPU path needs for one scene: stages + GP regions over a process
-    pool.  Regions are run in loop order until `budget_s` is spent; the rest is extrapolated by
-    sum(M^3).  Returns (seconds, description)."""
+def _cpu_cost_model(m):
+    """Rough single-core seconds of one 50-step fit with M rows (launch-overhead, M^2 and M^3 terms; SURVEY section 6
+    figures).  Only used as the size measure of the ratio estimator below - a constant factor cancels."""
+    m = np.asarray(m, dtype=np.float64)
+    return 0.15 + 2e-6 * m ** 2 + 2e-9 * m ** 3
+
+
+def cpu_scene_sample(inp, budget_s, pool, n_workers, rng):
+    """One bounded step of the CPU arm on one scene: the scene-level stages are timed in full; the GP regions are
+    timed on a RANDOM subset (a prefix of a random permutation, so it is a uniform sample whatever its length)
+    that fits the budget.  Returns (seconds spent, fraction of the scene's work that was done)."""
     from oracle import gen_ps_oracle as O
     jobs = []
 
@@ -97,19 +123,22 @@ def cpu_scene_time(inp, budget_s, pool, n_workers):
                               inp["instance_box_volume"].astype(np.float32), inp["wall_box"], inp["wall_volume"],
                               thresh_spp_occu=0.999, fit_fn=record)
     t_stage = time.perf_counter() - t0
-    m3 = np.array([float(len(j[0])) ** 3 for j in jobs])
+    if not jobs:
+        return t_stage, 1.0, 0, 0
+    cost = _cpu_cost_model([len(j[0]) for j in jobs])
+    order = rng.permutation(len(jobs))
     done, t_reg = 0, 0.0
-    group = max(n_workers * 2, 1)
-    while done < len(jobs) and t_reg < budget_s:
+    group = max(n_workers, 1)
+    while done < len(jobs) and (done == 0 or t_reg < budget_s - t_stage):
+        sel = order[done:done + group]
         t1 = time.perf_counter()
-        list(pool.imap_unordered(_fit_one, jobs[done:done + group]))
+        list(pool.imap_unordered(_fit_one, [jobs[i] for i in sel]))
         t_reg += time.perf_counter() - t1
-        done += min(group, len(jobs) - done)
-    frac = m3[:done].sum() / m3.sum() if len(jobs) else 1.0
-    total = t_stage + (t_reg / frac if frac > 0 else 0.0)
-    desc = (f"1 scene of the batch (N={len(inp['xyz'])}): stages timed in full, first {done} of {len(jobs)} GP regions "
-            f"timed ({100 * frac:.0f}% of sum M^3) on a {n_workers}-process pool, remainder extrapolated by sum M^3")
-    return total, desc
+        done += len(sel)
+    frac_gp = cost[order[:done]].sum() / cost.sum()
+    spent = t_stage + t_reg
+    est_full = t_stage + t_reg / frac_gp            # ratio estimator of the scene's full CPU time
+    return spent, spent / est_full, done, len(jobs)
 
 
 def run_reference(args):
@@ -118,25 +147,33 @@ def run_reference(args):
         return
     import multiprocessing as mp
     n_workers = len(os.sched_getaffinity(0))
-    inp = make_inputs(0, 1, args.workload)[0]
-    budget = max(3.0, min(25.0, 150.0 / max(args.steps + args.warmup, 1)))
+    ids = scene_ids(args, world)
+    budget = max(4.0, min(30.0, 150.0 / max(args.steps + args.warmup, 1)))
     ctx = mp.get_context("fork")
+    rng = np.random.default_rng(0)
+    spent, fracs, log = [], [], []
     with ctx.Pool(n_workers, initializer=_warm_worker) as pool:
         pool.map(_noop, range(4 * n_workers))      # returns once every worker has finished its initializer
-        times = []
-        desc = ""
         for s in range(args.warmup + args.steps):
-            t, desc = cpu_scene_time(inp, budget, pool, n_workers)
+            idx = ids[(s * 5) % len(ids)]          # stride 5: the steps walk over the whole scene list
+            t, f, done, total = cpu_scene_sample(make_input(idx, args.workload), budget, pool, n_workers, rng)
             if s >= args.warmup:
-                times.append(t)
-    sec = float(np.mean(times))
-    val = 1.0 / sec
+                spent.append(t)
+                fracs.append(f)
+                log.append(f"scene {idx}: {done}/{total} regions")
+    val = float(np.sum(fracs) / np.sum(spent))     # scenes (fractions of scenes) labelled per second
+    desc = (f"each step = one scene of the job's list (stride 5 through it): its scene-level stages in full plus a "
+            f"uniform random subset of its GP regions on a {n_workers}-process pool, bounded to ~{budget:.0f} s; the "
+            f"fraction of the scene a step covers is time spent / (stages + region time / cost-model share of the "
+            f"subset); value = sum of fractions / sum of seconds; [{'; '.join(log[:6])}{' ...' if len(log) > 6 else ''}]")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "scenes/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 Cholesky/solve), CPU", "data": "synthetic",
-        "config": {"workload": WORKLOAD % args.scenes, "note": "CPU restatement (oracle/, gpytorch policy); "
-                   "the reference itself needs gpytorch + torch_scatter, not installable here"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(spent)) * 1e3, "higher_is_better": True,
+        "scaling": args.mode, "vs_baseline": None, "dtype": "f32 (f64 Cholesky/solve), CPU", "data": "synthetic",
+        "config": static_config(args, world),
+        "scene_fraction_per_step": float(np.mean(fracs)),
+        "note": "CPU restatement of the reference (oracle/, gpytorch precision policy); the reference itself needs "
+                "gpytorch + torch_scatter, not installable here (DESIGN.md)",
         "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": n_workers, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -263,22 +300,23 @@ _RESULT_OUT = sys.stdout
 PHASE_ID = {"A": 2, "B": 3, "GA": 5, "GT": 6, "GC": 8, "GL": 9, "Y": 11, "GK": 12}
 
 
-def ncu_traffic(phase, args):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this workload (profiles/r01_traffic.json, written by profiles/summarize.py);
-    null when the capture is of another workload."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
-    try:
-        with open(path) as f:
-            t = json.load(f)
-    except OSError:
-        return None, "no ncu capture committed"
-    if t.get("workload") != f"{args.workload} x {args.scenes}":
-        return None, f"committed capture is of '{t.get('workload')}'"
-    k = t["kernels"].get(f"k_gemm<{PHASE_ID.get(phase, -1)}>")
-    if not k:
-        return None, "kernel not in the committed capture"
-    return k["dram_read_bytes"] + k["dram_write_bytes"], f"profiles/r01_traffic.json ({t.get('command', 'ncu --set full')})"
+def ncu_traffic(kernel_regex, args):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r02_traffic.json, written by profiles/summarize.py); null when there is no
+    capture of this workload."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            with open(path) as f:
+                t = json.load(f)
+        except OSError:
+            continue
+        if not str(t.get("workload", "")).startswith(args.workload):
+            continue
+        for k, v in t["kernels"].items():
+            if kernel_regex in k:
+                return v["dram_read_bytes"] + v["dram_write_bytes"], f"profiles/{name}: {k} ({t.get('command', 'ncu --set full')})"
+    return None, "no ncu capture of this workload committed"
 
 
 def run_gpu(args):
@@ -288,15 +326,12 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from gapro_b200 import _lib
-    from gapro_b200.engine import get_engine
+    from gapro_b200 import _lib, sharding
+    from gapro_b200.engine import SceneInputs, get_engine
     from gapro_b200.gen_ps import to_scene_inputs
     lib = _lib.load()
     eng = get_engine(dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
-
-    inps = make_inputs(rank, args.scenes, args.workload)
-    scenes = [to_scene_inputs(inp, dev, noise_seed=rank * 1000 + i) for i, inp in enumerate(inps)]
     kw = dict(thresh_spp_occu=0.999, training_iter=50)      # gen_ps.py:106-110
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush = lambda: flush_buf.zero_()
@@ -306,45 +341,84 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def max_over_ranks(x):
+    def gather_floats(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
-            t = torch.tensor([x], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return x
+            out = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(out, t)
+            return [float(o.item()) for o in out]
+        return [float(x)]
 
+    # ---- the job: a fixed scene list, sharded by estimated cost (the CLI's path: gapro_b200/gen_ps.py) -------
+    ids = scene_ids(args, world)
+    if world > 1:
+        # cost pass: every rank runs the cheap stages (U, F, A, A', P) on a round-robin share, one gather of the
+        # estimates, LPT on every rank (deterministic)
+        mine = ids[rank::world]
+        est = {}
+        for i0 in range(0, len(mine), args.scenes):
+            part = mine[i0:i0 + args.scenes]
+            st = eng.run([to_scene_inputs(make_input(i, args.workload), dev) for i in part], plan_only=True, **kw)
+            for k, i in enumerate(part):
+                est[i] = sharding.scene_cost(st["sum_m3"][k], st["n_points"][k], st["n_regions"][k])
+        merged = {}
+        for d in sharding.gather_records([est], world):
+            merged.update(d)
+        costs = [merged[i] for i in ids]
+        assign = sharding.lpt_assignment(costs, world)
+        est_balance = sharding.balance_stats(costs, assign)["max_over_mean"]
+        my_ids = [ids[k] for k in assign[rank]]
+    else:
+        my_ids, est_balance = ids, 1.0
+    inps = [make_input(i, args.workload) for i in my_ids]
+    scenes = [to_scene_inputs(inp, dev, noise_seed=1000 + i) for i, inp in zip(my_ids, inps)]
+    passes = [scenes[i:i + args.scenes] for i in range(0, len(scenes), args.scenes)]
+
+    def step():
+        outs = []
+        for p in passes:
+            flush()
+            outs.extend(eng.run(p, **kw))
+        return outs
+
+    launches_per_step = 0
     for _ in range(args.warmup):
-        flush()
-        eng.run(scenes, **kw)
-    launches_per_step = eng.last_stats["launches"]
+        step()
+    # launches of one step (counted by the library for the GP stage, by the host mirror for the rest)
+    for p in passes:
+        eng.run(p, **kw)
+        launches_per_step += eng.last_stats["launches"]
+    stats = [dict(eng.last_stats)]
 
     # ---- device-resident timing (value) ---------------------------------------------------------
     sampler = ClockSampler(local)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    hist = None
     for _ in range(args.steps):
-        flush()
-        outs = eng.run(scenes, **kw)
+        outs = step()
+    e_work = torch.cuda.Event(enable_timing=True)
+    e_work.record()
     # the one collective of the job: gather of label metadata (per-rank semantic histogram)
-    sem_all = torch.cat([o[0] for o in outs]).long()
-    hist = torch.bincount(torch.where(sem_all < 0, 19, sem_all), minlength=20)
+    if outs:
+        sem_all = torch.cat([o[0] for o in outs]).long()
+        hist = torch.bincount(torch.where(sem_all < 0, 19, sem_all), minlength=20)
+    else:
+        hist = torch.zeros(20, dtype=torch.long, device=dev)
     if world > 1:
         gathered = [torch.empty_like(hist) for _ in range(world)]
         dist.all_gather(gathered, hist)
         hist = torch.stack(gathered).sum(0)
     e1.record()
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    rank_ms = gather_floats(e0.elapsed_time(e_work) / args.steps)     # every rank's own work per step
+    ms_total = max(gather_floats(e0.elapsed_time(e1)))
     clocks = sampler.stop()
     ms_step = ms_total / args.steps
-    value = world * args.scenes / (ms_step * 1e-3)
-    stats = dict(eng.last_stats)
+    value = len(ids) / (ms_step * 1e-3)
 
     # ---- end to end: pinned host inputs -> device -> hot path -> host ----------------------------
-    pinned = []
-    h2d = 0
+    pinned, h2d = [], 0
     for inp in inps:
         d = {}
         for k, dt in (("xyz", torch.float64), ("mask_feats", torch.float32), ("spp", torch.int64),
@@ -354,44 +428,49 @@ def run_gpu(args):
             d[k] = t
             h2d += t.numel() * t.element_size()
         pinned.append(d)
-    from gapro_b200.engine import SceneInputs
 
     def e2e_step():
-        sc = []
-        for i, d in enumerate(pinned):
-            g = {k: v.to(dev, non_blocking=True) for k, v in d.items()}
-            sc.append(SceneInputs(g["xyz"], g["mask_feats"], g["spp"], g["instance_cls"], g["instance_box"],
-                                  g["instance_box_volume"], g["wall_box"], g["wall_volume"], noise_seed=rank * 1000 + i))
-        res = eng.run(sc, **kw)
-        host = [[t.to("cpu", non_blocking=True) for t in r] for r in res]
+        host = []
+        for i0 in range(0, len(pinned), args.scenes):
+            flush()
+            sc = []
+            for k, d in enumerate(pinned[i0:i0 + args.scenes]):
+                g = {kk: v.to(dev, non_blocking=True) for kk, v in d.items()}
+                sc.append(SceneInputs(g["xyz"], g["mask_feats"], g["spp"], g["instance_cls"], g["instance_box"],
+                                      g["instance_box_volume"], g["wall_box"], g["wall_volume"],
+                                      noise_seed=1000 + my_ids[i0 + k]))
+            res = eng.run(sc, **kw)
+            host.extend([t.to("cpu", non_blocking=True) for t in r] for r in res)
         return host
 
-    flush()
     host = e2e_step()
     torch.cuda.synchronize(dev)
     d2h = sum(t.numel() * t.element_size() for r in host for t in r)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
     barrier()
     e0.record()
     t_wall = time.perf_counter()
-    for _ in range(args.steps):
-        flush()
+    for _ in range(e2e_steps):
         e2e_step()
     e1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall
-    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), t_wall * 1e3)) / args.steps
-    e2e_val = world * args.scenes / (ms_e2e * 1e-3)
+    ms_e2e = max(gather_floats(max(e0.elapsed_time(e1), t_wall * 1e3))) / e2e_steps
+    e2e_val = len(ids) / (ms_e2e * 1e-3)
+    h2d_all = sum(gather_floats(float(h2d)))
+    d2h_all = sum(gather_floats(float(d2h)))
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (profiled step, outside the timed regions) ---------------
+    # ---- roofline of the dominant kernel (profiled pass, outside the timed regions) ---------------
     import ctypes
     lib.gapro_gp_set_profiling(1)
     flush()
-    eng.run(scenes, keep=True, **kw)
+    eng.run(passes[0], keep=True, **kw)
+    st0 = dict(eng.last_stats)
     n_slots = 17
     ms = (ctypes.c_double * n_slots)()
     fa = (ctypes.c_double * n_slots)()
@@ -410,30 +489,55 @@ def run_gpu(args):
     _lib.check(lib.gapro_fp64_peak(0, 20000, ctypes.byref(peak_dfma), scratch.data_ptr(), stream), "fp64 peak")
     peak = max(peak_dmma.value, peak_dfma.value)
     iters = 50
-    n_launch_top = iters       # one launch of this phase per training step (+ none in predict for most)
-    ach = phases[top]["alg_gflop"] / 1e3 / (phases[top]["ms"] * 1e-3)
+    ach = phases[top]["alg_gflop"] / 1e3 / max(phases[top]["ms"] * 1e-3, 1e-9)
     fam_ms = sum(phases[n]["ms"] for n in gemm_names)
     fam_alg = sum(phases[n]["alg_gflop"] for n in gemm_names) / 1e3
     fam_exe = sum(phases[n]["exe_gflop"] for n in gemm_names) / 1e3
     roofline = {
         "bound": "tensor", "kernel": f"k_gemm<{top}> (FP64 DMMA tile kernel)", "achieved": ach, "peak": peak,
         "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-        "peak_source": "in-repo FP64 microbenchmark gapro_fp64_peak (DMMA %.1f / DFMA %.1f TFLOP/s); "
-                       "MEASURED_PEAKS.json has no FP64 figure" % (peak_dmma.value, peak_dfma.value),
-        "avg_launch_ms": phases[top]["ms"] / n_launch_top, "share_of_step": phases[top]["ms"] / (ms_step),
-        "gemm_family": {"ms": fam_ms, "share_of_step": fam_ms / ms_step, "achieved_alg": fam_alg / (fam_ms * 1e-3),
-                        "achieved_issued": fam_exe / (fam_ms * 1e-3), "frac_alg": fam_alg / (fam_ms * 1e-3) / peak,
-                        "frac_issued": fam_exe / (fam_ms * 1e-3) / peak},
+        "peak_source": "in-repo FP64 microbenchmark gapro_fp64_peak on this GPU (DMMA %.1f / DFMA %.1f TFLOP/s); "
+                       "MEASURED_PEAKS.json has no FP64 figure; cross-check: B200 FP64 datasheet figure 37-40 TFLOP/s "
+                       "(SURVEY.md section 7), i.e. measured / spec = %.2f-%.2f"
+                       % (peak_dmma.value, peak_dfma.value, peak / 40.0, peak / 37.0),
+        "avg_launch_ms": phases[top]["ms"] / iters,
+        "profiled_pass": "first pass of rank 0 (%d scenes, sum M^3 = %.3g), phases timed on one stream"
+                         % (len(passes[0]), st0["sum_m3"]),
+        "gemm_family": {"ms": fam_ms, "share_of_gp_stage": fam_ms / max(gp_ms, 1e-9),
+                        "achieved_alg": fam_alg / max(fam_ms * 1e-3, 1e-9), "achieved_issued": fam_exe / max(fam_ms * 1e-3, 1e-9),
+                        "frac_alg": fam_alg / max(fam_ms * 1e-3, 1e-9) / peak,
+                        "frac_issued": fam_exe / max(fam_ms * 1e-3, 1e-9) / peak},
         "gp_stage_ms": gp_ms, "phases_ms": {n: round(phases[n]["ms"], 3) for n in names},
     }
-    roofline["traffic"], roofline["traffic_source"] = ncu_traffic(top, args)
+    roofline["traffic"], roofline["traffic_source"] = ncu_traffic(f"k_gemm<{PHASE_ID.get(top, -1)}>", args)
     stages = stage_rooflines(eng, lib, stream, flush)
-    # the same kernels on a batch large enough to amortise launch latency (the step's scenes, 8 times over)
-    eng.run(scenes * 8, stages_only=True, **kw)
+    # the same kernels on a batch large enough to amortise launch latency (the pass's scenes, 8 times over)
+    eng.run(passes[0] * 8, stages_only=True, **kw)
     stages_large = stage_rooflines(eng, lib, stream, flush)
     for v in stages_large.values():
         v["points"] = eng.last["N"]
     eng.last = None
+
+    # ---- single-scene latency through the reference's per-scene call (BASELINE configs[1]) ---------
+    latency = None
+    if world == 1 and not args.no_latency:
+        from gapro_b200.gen_ps_utils import gen_pseudo_label_gaussian_process
+        sc = to_scene_inputs(make_input(0, "c1"), dev, noise_seed=1)
+        ts = []
+        for r in range(4):
+            flush()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            out = gen_pseudo_label_gaussian_process(sc.coords_float, sc.mask_feats, sc.spp, sc.instance_cls,
+                                                    sc.instance_box, sc.instance_box_volume, sc.wall_box,
+                                                    sc.wall_box_volume, instance_classes=18, dataset_name="scannetv2",
+                                                    ground_h=0.1, training_iter=50, thresh_spp_occu=0.999, noise_seed=1)
+            torch.cuda.synchronize(dev)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        latency = {"workload": WORKLOADS["c1"] + ", ONE scene through gen_pseudo_label_gaussian_process "
+                   "(gen_ps_utils.py:293), device-resident inputs, wall clock with a synchronize on both sides",
+                   "ms": float(np.median(ts[1:])), "first_call_ms": ts[0], "gp_regions": eng.last_stats["n_regions"],
+                   "launches": eng.last_stats["launches"]}
 
     # ---- CPU baseline (bounded sample) -------------------------------------------------------------
     cpu = None
@@ -441,29 +545,32 @@ def run_gpu(args):
         # fresh interpreter with the GPUs hidden: this process holds a CUDA context and must not fork workers
         env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
-                                "--warmup", "0", "--workload", args.workload, "--scenes", str(args.scenes)],
-                               env=env, capture_output=True, text=True, timeout=240)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
+                                "--warmup", "0", "--workload", args.workload, "--scenes", str(args.scenes),
+                                "--mode", args.mode, "--total-scenes", str(args.total_scenes)],
+                               env=env, capture_output=True, text=True, timeout=300)
             cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as e:      # reported, never fatal for the GPU line
             cpu = {"value": None, "unit": "scenes/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
                    "sample": "CPU baseline run failed: %r" % (e,)}
 
+    mean_ms = sum(rank_ms) / len(rank_ms)
     line = {
         "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.mode,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD % args.scenes, "scenes_per_gpu_per_step": args.scenes,
-                   "points_per_step_per_gpu": stats["n_points"], "superpoints": stats["n_spp"],
-                   "gp_regions_per_step_per_gpu": stats["n_regions"], "sum_M": stats["sum_m"],
-                   "gp_iters": 50, "l2": "256 MiB buffer written between steps (flush)",
-                   "label_histogram_points": int(hist.sum().item())},
-        "gp_regions_per_s": world * stats["n_regions"] / (ms_step * 1e-3),
-        "e2e": {"value": e2e_val, "unit": "scenes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e},
+        "config": static_config(args, world),
+        "workload_stats": {"scenes_this_rank": len(my_ids), "passes_per_step_this_rank": len(passes),
+                           "label_histogram_points": int(hist.sum().item()),
+                           "first_pass": {"points": st0["n_points"], "superpoints": st0["n_spp"],
+                                          "gp_regions": st0["n_regions"], "sum_M": st0["sum_m"], "sum_M3": st0["sum_m3"]}},
+        "balance": {"rank_ms_per_step": [round(x, 2) for x in rank_ms], "max_over_mean": max(rank_ms) / mean_ms,
+                    "estimated_max_over_mean": est_balance},
+        "e2e": {"value": e2e_val, "unit": "scenes/s", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
+                "ms_per_step": ms_e2e, "steps": e2e_steps},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks, "roofline": roofline, "stage_rooflines": stages, "stage_rooflines_large_batch": stages_large,
-        "cpu_baseline": cpu,
+        "latency": latency, "cpu_baseline": cpu,
     }
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
@@ -476,9 +583,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scenes", type=int, default=8, help="scenes per GPU per step")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c1_deep", "c4", "c5", "small", "tiny"])
+    ap.add_argument("--mode", default="strong", choices=["strong", "weak"],
+                    help="strong: a fixed list of --total-scenes scenes sharded over the GPUs; weak: --scenes per GPU")
+    ap.add_argument("--total-scenes", type=int, default=32, help="scenes of the job (strong mode)")
+    ap.add_argument("--scenes", type=int, default=8, help="scenes per GPU pass (and per GPU per step in weak mode)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=5, help="steps of the end-to-end timing (at most --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON); whatever libraries print there (NCCL prints its version banner
     # to stdout at communicator creation) goes to stderr instead

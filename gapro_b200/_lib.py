@@ -39,6 +39,7 @@ _SIGNATURES = {
     "gapro_gp_fit_batch": (ctypes.c_int, [P, c_int32, c_int32, P, P, P, P, P, P, c_int32, c_double, c_double,
                                           c_double, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     "gapro_gp_last_launch_count": (c_int64, []),
+    "gapro_gp_debug_aux_slack": (c_int64, [c_int32, P, P, c_int32]),
     "gapro_gp_set_profiling": (ctypes.c_int, [ctypes.c_int]),
     "gapro_gp_phase_names": (c_char_p, []),
     "gapro_gp_get_profile": (ctypes.c_int, [P, P, P, c_int32]),

@@ -1641,6 +1641,42 @@ extern "C" size_t gapro_gp_min_workspace_bytes(int32_t n_regions, const int32_t*
 
 extern "C" int64_t gapro_gp_last_launch_count(void) { return g_launches; }
 
+// Host-only replay of the workspace arithmetic (no CUDA call): the regions are split round-robin over `groups`
+// stream groups exactly as run_regions does; returns (bytes aux_bytes() reserves for the whole chunk) - (bytes the
+// groups' tile tables take with their per-table alignment).  Negative = the tables would overrun the workspace.
+extern "C" int64_t gapro_gp_debug_aux_slack(int32_t n_regions, const int32_t* train_off, const int32_t* test_off,
+                                            int32_t groups) {
+    if (n_regions <= 0 || !train_off || !test_off || groups < 1) return 0;
+    std::vector<Region> rs = sorted_regions(n_regions, train_off, nullptr, test_off);
+    std::vector<std::vector<Region>> gs(groups);
+    for (size_t i = 0; i < rs.size(); ++i) gs[i % groups].push_back(rs[i]);
+    const int sg = sweep_group_size();
+    int64_t used = 0;
+    for (const std::vector<Region>& g : gs) {
+        if (g.empty()) continue;
+        size_t full = 0, lower = 0, wide = 0, rows = 0, rowsp = 0, panel = 0, upd = 0;
+        for (const Region& r : g) {
+            full += (size_t)r.nb * r.nb;
+            lower += (size_t)r.nb * (r.nb + 1) / 2;
+            wide += (size_t)r.nb * r.nbw;
+            rows += r.nb;
+            for (int t = 0; t < r.Np / TB; ++t) rowsp += (t * TB < r.N);
+            panel += r.nb - 1;
+            for (int kb = 0; kb < r.nb; ++kb) {
+                if (kb % sg == sg - 1) {
+                    for (int i = r.nb - 1; i > kb; --i) upd += i + 1;
+                } else if (kb + 1 < r.nb) {
+                    upd += (r.nb - 1 - kb) + (kb + 1);
+                }
+            }
+        }
+        const size_t sizes[8] = {g.size() * sizeof(Region), full * 16, lower * 16, wide * 16, rows * 8, rowsp * 8,
+                                 panel * 8, upd * 16};
+        for (size_t b : sizes) used += (int64_t)gapro_align_up(b ? b : 1, 256);
+    }
+    return (int64_t)aux_bytes(rs) - used;
+}
+
 // ---- side streams: independent region groups run concurrently so that the latency-bound
 // Cholesky sweep of one group overlaps the tile products of the others --------------------------------
 constexpr int MAX_GROUPS = 8;

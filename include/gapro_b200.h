@@ -222,6 +222,9 @@ int gapro_compact_lists(const uint32_t* occ_bits, const int32_t* n_bbs, const in
 size_t gapro_gp_workspace_bytes(int32_t n_regions, const int32_t* train_off, const int32_t* test_off, int32_t D);
 size_t gapro_gp_min_workspace_bytes(int32_t n_regions, const int32_t* train_off, const int32_t* test_off,
                                     int32_t D);
+/* host-only replay of the workspace layout for `groups` stream groups: reserved table bytes minus the bytes the
+ * groups' tables take (>= 0 unless the tables would overrun the workspace); no CUDA call, used by the CPU tests */
+int64_t gapro_gp_debug_aux_slack(int32_t n_regions, const int32_t* train_off, const int32_t* test_off, int32_t groups);
 int gapro_gp_fit_batch(const float* feats_spp, int32_t D, int32_t n_regions, const int32_t* train_off,
                        const int32_t* n_b1, const int32_t* test_off, const int32_t* train_idx,
                        const int32_t* test_idx, const float* init_noise, int32_t iters, double lr,

@@ -160,3 +160,21 @@ def test_errors_are_reported_not_fatal(lib):
     need = lib.gapro_gp_min_workspace_bytes(2, off.ctypes.data, toff.ctypes.data, 6)
     assert 0 < need <= full
     assert lib.gapro_densify_workspace_bytes(1000, 2) > 1000 * 28
+
+
+def test_gp_tile_tables_fit_the_advertised_workspace(lib):
+    """Round-1 advisor finding: the tile tables of a chunk split into stream groups overran
+    gapro_gp_workspace_bytes by ~50 KB for many small regions.  Host-side replay of the layout arithmetic for the
+    cases the advisor computed and a sweep of random region mixes, for every group count."""
+    rng = np.random.default_rng(0)
+    cases = [[100] * 16, [150] * 40, list(rng.integers(2, 400, 60)), [2] * 500, [64] * 33, [65, 1607, 3, 700] * 5]
+    cases += [list(rng.integers(1, 2000, int(rng.integers(1, 120)))) for _ in range(40)]
+    for ms in cases:
+        n = len(ms)
+        tr = np.zeros(n + 1, np.int32)
+        tr[1:] = np.cumsum(ms)
+        te = np.zeros(n + 1, np.int32)
+        te[1:] = np.cumsum(rng.integers(1, 300, n))
+        for groups in range(1, 9):
+            slack = lib.gapro_gp_debug_aux_slack(n, tr.ctypes.data, te.ctypes.data, groups)
+            assert slack >= 0, (ms[:8], groups, slack)

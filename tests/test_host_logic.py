@@ -140,6 +140,14 @@ def test_sharding_covers_every_scene_once():
     assert sorted(sum(parts, [])) == items
     loads = [sum(costs[items.index(x)] for x in p) for p in parts]
     assert max(loads) / (sum(loads) / 8) < 1.1        # LPT keeps the ranks balanced
+    # the job the bench shards: per-scene cost ~ sum M^3, heavy-tailed over orders of magnitude
+    c = sharding.COST_PER_M3 * np.random.default_rng(1).lognormal(23.0, 1.2, 1201)
+    for world in (2, 4, 8):
+        assign = sharding.lpt_assignment(c, world)
+        assert sorted(sum(assign, [])) == list(range(1201))
+        assert sharding.balance_stats(c, assign)["max_over_mean"] <= 1.05
+        assert all(list(c[a]) == sorted(c[a], reverse=True) for a in assign)       # heavy scenes first
+    assert sharding.scene_cost(1e10, 150_000, 40) > sharding.scene_cost(1e9, 150_000, 40) > 0
 
 
 WORKER = r"""
@@ -153,6 +161,16 @@ mine = sharding.shard_scenes(items, dist.get_rank(), 2)
 records = sharding.gather_records([(s, len(s), dist.get_rank()) for s in mine], 2)
 assert sorted(r[0] for r in records) == items, records
 assert {{r[2] for r in records}} == {{0, 1}}
+# the cost pass of the CLI / bench: every rank estimates its round-robin share, ONE gather, LPT on every rank
+est = {{s: float(int(s[5:9]) % 7 + 1) for s in items[dist.get_rank()::2]}}
+merged = {{}}
+for d in sharding.gather_records([est], 2):
+    merged.update(d)
+costs = [merged[s] for s in items]
+assign = sharding.lpt_assignment(costs, 2)
+both = sharding.gather_records([assign], 2)
+assert both[0] == both[1] and sorted(assign[0] + assign[1]) == list(range(11))
+assert sharding.balance_stats(costs, assign)["max_over_mean"] < 1.1
 dist.barrier()
 dist.destroy_process_group()
 print("ok")
