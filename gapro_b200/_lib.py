@@ -26,6 +26,9 @@ _SIGNATURES = {
     "gapro_floor_boxes": (ctypes.c_int, [P, P, P, c_int32, c_int64, c_double, P, P, P, P]),
     "gapro_occupancy": (ctypes.c_int, [P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_double, c_float,
                                        P, P, P, P, P, P]),
+    "gapro_occupancy_points_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "gapro_occupancy_points": (ctypes.c_int, [P, P, P, P, P, P, P, P, c_int32, c_int64, c_int32, c_int32, c_int32,
+                                              c_double, c_float, P, P, P, P, P, P, c_size_t, P]),
     "gapro_heuristic_labels": (ctypes.c_int, [P, P, P, P, P, P, P, P, c_int32, c_int32, c_int32, c_int32, c_int32,
                                               c_float, P, P, P]),
     "gapro_multibox_workspace_bytes": (c_size_t, [c_int64]),

@@ -71,6 +71,11 @@ class GaproEngine:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.gp_workspace_cap = gp_workspace_bytes
         self._ws = {}
+        # "points" (default): A + A' stream the points in input order; "gather": the by-superpoint kernel of round 1
+        import os
+        self.occupancy_path = os.environ.get("GAPRO_OCCUPANCY", "points")
+        if self.occupancy_path not in ("points", "gather"):
+            raise ValueError("GAPRO_OCCUPANCY must be 'points' or 'gather'")
 
     # ------------------------------------------------------------------ helpers
     def _workspace(self, key: str, nbytes: int) -> torch.Tensor:
@@ -172,16 +177,30 @@ class GaproEngine:
         # ---- A + A': containment / occupancy ----------------------------------------------
         occ_bits = torch.empty((St, words), dtype=torch.int32, device=dev)
         n_bbs = torch.empty(St, dtype=torch.int32, device=dev)
-        cnt_in = torch.empty((St, 32 * words), dtype=torch.int32, device=dev) if want_cnt_in else None
         excl_cnt = torch.empty(Bt, dtype=torch.int32, device=dev)
         stride = 32 * words
         inter_cnt = torch.empty((ns, stride, stride), dtype=torch.int32, device=dev)
-        _lib.check(lib.gapro_occupancy(xyz.data_ptr(), perm.data_ptr(), seg_off.data_ptr(), spp_off_dev.data_ptr(),
-                                       box_off_dev.data_ptr(), boxes.data_ptr(), ns, St, Bt, words, MARGIN,
-                                       float(np.float32(thresh_spp_occu)), occ_bits.data_ptr(), n_bbs.data_ptr(),
-                                       _ptr(cnt_in), excl_cnt.data_ptr(), inter_cnt.data_ptr(), stream),
-                   "gapro_occupancy")
-        n_launch += 1
+        thresh32 = float(np.float32(thresh_spp_occu))
+        if self.occupancy_path == "points":
+            # point order: stream xyz + dense ids, per-scene grid of box masks, integer counts in L2
+            cnt_in = torch.empty((St, stride), dtype=torch.int32, device=dev)
+            ows = self._workspace("occ", lib.gapro_occupancy_points_workspace_bytes(ns, words))
+            _lib.check(lib.gapro_occupancy_points(xyz.data_ptr(), spp_gid.data_ptr(), seg_off.data_ptr(),
+                                                  pt_off_dev.data_ptr(), spp_off_dev.data_ptr(), box_off_dev.data_ptr(),
+                                                  boxes.data_ptr(), scratch.data_ptr(), ns, N, St, Bt, words, MARGIN,
+                                                  thresh32, occ_bits.data_ptr(), n_bbs.data_ptr(), cnt_in.data_ptr(),
+                                                  excl_cnt.data_ptr(), inter_cnt.data_ptr(), ows.data_ptr(), ows.numel(),
+                                                  stream), "gapro_occupancy_points")
+            n_launch += 3
+        else:
+            # by superpoint: gather through the sort permutation (round-1 kernel, kept for comparison)
+            cnt_in = torch.empty((St, stride), dtype=torch.int32, device=dev) if want_cnt_in else None
+            _lib.check(lib.gapro_occupancy(xyz.data_ptr(), perm.data_ptr(), seg_off.data_ptr(), spp_off_dev.data_ptr(),
+                                           box_off_dev.data_ptr(), boxes.data_ptr(), ns, St, Bt, words, MARGIN,
+                                           thresh32, occ_bits.data_ptr(), n_bbs.data_ptr(),
+                                           _ptr(cnt_in), excl_cnt.data_ptr(), inter_cnt.data_ptr(), stream),
+                       "gapro_occupancy")
+            n_launch += 1
 
         # ---- B: feature pooling ------------------------------------------------------------
         feats_spp = torch.empty((St, D), dtype=torch.float32, device=dev)
@@ -192,7 +211,8 @@ class GaproEngine:
         if stages_only:      # benchmarking hook: stop after the memory-bound stages, keep their buffers
             self.last = dict(xyz=xyz, feats=feats, perm=perm, seg_off=seg_off, spp_gid=spp_gid, spp_off_dev=spp_off_dev,
                              box_off_dev=box_off_dev, boxes=boxes, occ_bits=occ_bits, n_bbs=n_bbs, excl_cnt=excl_cnt,
-                             inter_cnt=inter_cnt, feats_spp=feats_spp,
+                             inter_cnt=inter_cnt, feats_spp=feats_spp, pt_off_dev=pt_off_dev, scratch=scratch,
+                             cnt_in=cnt_in,
                              packed_spp=torch.zeros((St, 4), dtype=torch.int32, device=dev),
                              sem=torch.empty(N, dtype=torch.int32, device=dev),
                              inst=torch.empty(N, dtype=torch.int32, device=dev),
@@ -304,7 +324,8 @@ class GaproEngine:
         if keep:
             self.last = dict(xyz=xyz, feats=feats, perm=perm, seg_off=seg_off, spp_gid=spp_gid, spp_off_dev=spp_off_dev,
                              box_off_dev=box_off_dev, boxes=boxes, occ_bits=occ_bits, n_bbs=n_bbs, excl_cnt=excl_cnt,
-                             inter_cnt=inter_cnt, feats_spp=feats_spp, packed_spp=packed_spp, sem=sem, inst=inst, prob=prob, ns=ns, St=St, Bt=Bt, N=N, D=D,
+                             inter_cnt=inter_cnt, feats_spp=feats_spp, pt_off_dev=pt_off_dev, scratch=scratch,
+                             cnt_in=cnt_in, packed_spp=packed_spp, sem=sem, inst=inst, prob=prob, ns=ns, St=St, Bt=Bt, N=N, D=D,
                              words=words, thresh=float(np.float32(thresh_spp_occu)))
         out = []
         for i in range(ns):

@@ -298,6 +298,25 @@ int gapro_broadcast_labels(const int32_t* spp_gid, int64_t n_points, const void*
                            int32_t* inst, float* prob, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * A + A' in point order (the default path).  Same results as gapro_occupancy - containment
+ * gen_ps_utils.py:349-351 (float64 compares on the float64 boxes, margin 0.005), occupancy pooling :359-363
+ * (integer counts, one float32 divide, >= thresh), n_bbs :363 - but xyz and the dense ids are streamed in point
+ * order instead of being gathered by superpoint: a per-scene 32x32x8 grid of box masks decides most boxes per
+ * cell, the exact test runs only for boxes whose boundary crosses the point's cell, counts go to `cnt_table` with
+ * integer reductions.
+ *   spp_gid dev int32[n_points] (gapro_densify_spp); extent_keys: the scratch gapro_floor_boxes filled
+ *   (per scene min xyz, max xyz as order-preserving uint64 keys); cnt_table dev int32[S_total, 32*words]
+ *   (points of superpoint s inside box b, kept as an output); the other outputs as gapro_occupancy.
+ */
+size_t gapro_occupancy_points_workspace_bytes(int32_t n_scenes, int32_t words);
+int gapro_occupancy_points(const double* xyz, const int32_t* spp_gid, const int32_t* seg_off, const int64_t* pt_off_dev,
+                           const int32_t* spp_off_dev, const int32_t* box_off_dev, const double* boxes,
+                           const uint64_t* extent_keys, int32_t n_scenes, int64_t n_points, int32_t s_total,
+                           int32_t n_boxes, int32_t words, double margin, float thresh, uint32_t* occ_bits,
+                           int32_t* n_bbs, int32_t* cnt_table, int32_t* excl_cnt, int32_t* inter_cnt, void* ws,
+                           size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Ev — pseudo-label quality (`--eval_pslabel`, gen_ps.py:116-124).  Replaces
  * get_miou_scene (eval_ps_labels.py:100-147): for every ground-truth instance id g in [0, n_gt) the best IoU
  * with a pseudo instance of the same class (class of an instance = semantic label of its first point; IoU in
