@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgapro_b200.so")
-SOURCES = ["capi.cu", "scene_kernels.cu", "gp_fit.cu", "eval_kernels.cu", "occupancy_points.cu"]
+SOURCES = ["capi.cu", "scene_kernels.cu", "gp_fit.cu", "eval_kernels.cu", "occupancy_points.cu", "ozaki.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -317,6 +317,18 @@ int gapro_occupancy_points(const double* xyz, const int32_t* spp_gid, const int3
                            size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Float64 products on tcgen05 by int8 digit planes ("Ozaki scheme"; csrc/ozaki.cu).  C[M,N] = op(A) op(B)^T:
+ * trans = 0 - the operand is stored [vectors, K] row-major, trans = 1 - [K, vectors] row-major; kscale (optional,
+ * dev double[K]) multiplies the A operand along k (A diag(kscale) B^T, the dT product of the GP step).  S digits per
+ * operand (2..7; 6 gives ~1e-12 of the row-norm bound), S(S+1)/2 int8 products.  ws 1024-byte aligned.  The last of
+ * `reps` runs is timed with CUDA events: ms_slice (scaling + digit planes), ms_gemm (the tcgen05 kernel).
+ */
+size_t gapro_ozaki_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t S);
+int gapro_ozaki_gemm(const double* A, int32_t lda, int32_t transA, const double* kscale, const double* B, int32_t ldb,
+                     int32_t transB, int32_t M, int32_t N, int32_t K, int32_t S, double* C, int32_t ldc, void* ws,
+                     size_t ws_bytes, int32_t reps, float* ms_slice, float* ms_gemm, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Ev — pseudo-label quality (`--eval_pslabel`, gen_ps.py:116-124).  Replaces
  * get_miou_scene (eval_ps_labels.py:100-147): for every ground-truth instance id g in [0, n_gt) the best IoU
  * with a pseudo instance of the same class (class of an instance = semantic label of its first point; IoU in
