@@ -259,10 +259,19 @@ def stage_rooflines(eng, lib, stream, flush):
             ts.append(a.elapsed_time(b))
         return float(np.median(ts))
 
-    occ = lambda: _lib.check(lib.gapro_occupancy(
+    occ_gather = lambda: _lib.check(lib.gapro_occupancy(
         L["xyz"].data_ptr(), L["perm"].data_ptr(), L["seg_off"].data_ptr(), L["spp_off_dev"].data_ptr(),
         L["box_off_dev"].data_ptr(), L["boxes"].data_ptr(), L["ns"], S, Bt, words, 0.005, L["thresh"],
         L["occ_bits"].data_ptr(), L["n_bbs"].data_ptr(), 0, L["excl_cnt"].data_ptr(), L["inter_cnt"].data_ptr(), stream), "occ")
+    ows = torch.empty(max(lib.gapro_occupancy_points_workspace_bytes(L["ns"], words), 256), dtype=torch.uint8,
+                      device=L["xyz"].device)
+    cnt_tab = L["cnt_in"] if L.get("cnt_in") is not None else torch.empty((S, 32 * words), dtype=torch.int32,
+                                                                          device=L["xyz"].device)
+    occ = lambda: _lib.check(lib.gapro_occupancy_points(
+        L["xyz"].data_ptr(), L["spp_gid"].data_ptr(), L["seg_off"].data_ptr(), L["pt_off_dev"].data_ptr(),
+        L["spp_off_dev"].data_ptr(), L["box_off_dev"].data_ptr(), L["boxes"].data_ptr(), L["scratch"].data_ptr(), L["ns"], N,
+        S, Bt, words, 0.005, L["thresh"], L["occ_bits"].data_ptr(), L["n_bbs"].data_ptr(), cnt_tab.data_ptr(),
+        L["excl_cnt"].data_ptr(), L["inter_cnt"].data_ptr(), ows.data_ptr(), ows.numel(), stream), "occ points")
     pool = lambda: _lib.check(lib.gapro_pool_feats(L["feats"].data_ptr(), L["perm"].data_ptr(), L["seg_off"].data_ptr(),
                                                    S, D, L["feats_spp"].data_ptr(), stream), "pool")
     bc = lambda: _lib.check(lib.gapro_broadcast_labels(L["spp_gid"].data_ptr(), N, L["packed_spp"].data_ptr(),
@@ -278,6 +287,8 @@ def stage_rooflines(eng, lib, stream, flush):
     out = {}
     for name, fn, nbytes in (
         ("containment+occupancy (A+A')", occ, N * (24 + 4) + 48 * Bt + 4 * S * words + 4 * S),
+        ("containment+occupancy, round-1 by-superpoint gather kernel (not on the path)", occ_gather,
+         N * (24 + 4) + 48 * Bt + 4 * S * words + 4 * S),
         ("feature pooling (B)", pool, N * (4 * D + 4) + 4 * S * D),
         ("broadcast (E)", bc, N * 4 + 16 * S + N * 12),
     ):
@@ -285,8 +296,9 @@ def stage_rooflines(eng, lib, stream, flush):
         gbs = nbytes / (ms * 1e-3) / 1e9
         out[name] = {"ms": ms, "algorithmic_bytes": int(nbytes), "achieved": gbs, "peak": peak, "unit": "GB/s",
                      "frac": gbs / peak, "peak_source": peak_src}
-    for name in ("containment+occupancy (A+A')", "feature pooling (B)"):
-        # both read N random 24-byte records + a coalesced index: the random-gather microbenchmark is their roofline
+    for name in ("feature pooling (B)",):
+        # reads N random 24-byte records + a coalesced index (index-ordered float32 sums need the points grouped by
+        # superpoint): the random-gather microbenchmark is shown next to the copy peak
         out[name]["random_gather_peak"] = g_gbs
         out[name]["frac_of_random_gather_peak"] = out[name]["achieved"] / g_gbs
     out["random 24-byte gather microbenchmark (gapro_gather_peak)"] = {

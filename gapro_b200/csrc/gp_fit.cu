@@ -58,8 +58,9 @@ struct Region {
     int n_b1;          // first n_b1 training rows carry label -1
     int train_off, test_off;
     int orig;          // index in the caller's region order
-    int pad_;
+    int oz;            // 1: the tile products of the training steps run on tcgen05 (gp_ozaki.cuh)
     long long base;    // offset of the region's buffers in the workspace, in doubles
+    long long oz_base; // offset of the digit-plane buffers (oz regions), in doubles
 };
 
 struct Layout {
@@ -433,6 +434,8 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
 }
 
 #undef KCLIP
+
+#include "gp_ozaki.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // kernel matrices: K_zz = s exp(-r2/2) + jitter I (lower tiles), K_zx = s exp(-r2/2)
@@ -1211,6 +1214,20 @@ k_region_init(const Region* __restrict__ regs, int D, const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 inline int ceil64(int x) { return (x + 63) / 64 * 64; }
 
+// ---- tcgen05 path configuration (development knobs; defaults are what the parity suite runs with) -----------
+static int oz_digits() {
+    int s = 6;      // 2^-42 truncation per operand: ~1e-12 normwise per product (ozaki.cu)
+    if (const char* e = getenv("GAPRO_GP_OZAKI_S")) s = atoi(e);
+    return s < 5 ? 5 : (s > 7 ? 7 : s);
+}
+static int oz_min_rows() {
+    int m = 1024;   // regions with at least this many (padded) training rows take the tcgen05 path
+    if (const char* e = getenv("GAPRO_GP_OZAKI_MIN_M")) m = atoi(e);
+    if (const char* e = getenv("GAPRO_GP_OZAKI"))
+        if (atoi(e) == 0) m = 1 << 30;
+    return m;
+}
+
 Region make_region(int M, int N, int n_b1, int train_off, int test_off, int orig) {
     Region r;
     r.M = M;
@@ -1224,33 +1241,79 @@ Region make_region(int M, int N, int n_b1, int train_off, int test_off, int orig
     r.train_off = train_off;
     r.test_off = test_off;
     r.orig = orig;
-    r.pad_ = 0;
+    r.oz = (r.Mp >= oz_min_rows() && M <= 8192) ? 1 : 0;      // K <= 8192 keeps the int32 accumulators exact
     r.base = 0;
+    r.oz_base = 0;
     return r;
 }
 
-size_t region_doubles(const Region& r, int D) {
+size_t region_core_doubles(const Region& r, int D) {
     return (size_t)gapro_align_up((size_t)make_layout(r.Mp, r.Np, r.Wp, D).total, 32);
 }
+size_t region_doubles(const Region& r, int D) {
+    size_t d = region_core_doubles(r, D);
+    if (r.oz) d += (size_t)gapro_align_up((size_t)oz_region_doubles(r.Mp, oz_digits()), 32);
+    return d;
+}
 
-// bytes of descriptors + tile tables for a set of regions
-size_t aux_bytes(const std::vector<Region>& rs) {
-    size_t full = 0, lower = 0, wide = 0, rows = 0, rowsp = 0, panel = 0, upd = 0;
+
+// Trailing updates of the sweep are applied `group` block steps at a time (contraction depth group * 64);
+// between two full passes only the next block column / block row is brought up to date.
+static int sweep_group_size() {
+    int g = 4;      // measured on the bench batch: 2 -> 1563 ms, 4 -> 1544 ms, 8 -> 1559 ms per step
+    if (const char* e = getenv("GAPRO_GP_SWEEP_GROUP")) g = atoi(e);
+    return g < 1 ? 1 : (g > 8 ? 8 : g);
+}
+
+// entries of every descriptor / tile table of a set of regions (exact; additive over regions)
+enum { TC_REGS = 0, TC_FULL, TC_LOWER, TC_WIDE, TC_ROWS, TC_ROWSP, TC_PANEL, TC_UPD, TC_FULL_S, TC_LOWER_S, TC_OZ_VB,
+       TC_OZ_BLK, TC_OZ_FULL, TC_OZ_LOWER, TC_COUNT };
+static const size_t TC_ELEM[TC_COUNT] = {sizeof(Region), 16, 16, 16, 8, 8, 8, 16, 16, 16, 8, 16, 16, 16};
+
+void count_tables(const std::vector<Region>& rs, size_t (&n)[TC_COUNT]) {
+    for (int i = 0; i < TC_COUNT; ++i) n[i] = 0;
+    const int sg = sweep_group_size();
+    n[TC_REGS] = rs.size();
     for (const Region& r : rs) {
-        full += (size_t)r.nb * r.nb;
-        lower += (size_t)r.nb * (r.nb + 1) / 2;
-        wide += (size_t)r.nb * r.nbw;
-        rows += r.nb;
-        rowsp += r.Np / TB;
-        panel += r.nb - 1;
-        upd += (size_t)(r.nb - 1) * r.nb * (r.nb + 1) / 3;      // sum_kb sum_{i>kb} (i+1)
+        const size_t full = (size_t)r.nb * r.nb, lower = (size_t)r.nb * (r.nb + 1) / 2;
+        n[TC_FULL] += full;
+        n[TC_LOWER] += lower;
+        n[TC_WIDE] += (size_t)r.nb * r.nbw;
+        n[TC_ROWS] += r.nb;
+        for (int t = 0; t < r.Np / TB; ++t) n[TC_ROWSP] += (t * TB < r.N);
+        n[TC_PANEL] += r.nb - 1;
+        for (int kb = 0; kb < r.nb; ++kb) {
+            if (kb % sg == sg - 1) {
+                for (int i = r.nb - 1; i > kb; --i) n[TC_UPD] += i + 1;
+            } else if (kb + 1 < r.nb) {
+                n[TC_UPD] += (r.nb - 1 - kb) + (kb + 1);
+            }
+        }
+        if (!r.oz) {
+            n[TC_FULL_S] += full;
+            n[TC_LOWER_S] += lower;
+        } else {
+            const int kbt = (r.M + 63) / 64, t128 = (r.M + 127) / 128;
+            n[TC_OZ_VB] += kbt;
+            n[TC_OZ_BLK] += (size_t)kbt * kbt;
+            n[TC_OZ_FULL] += (size_t)t128 * kbt;
+            for (int ti = 0; ti < t128; ++ti)
+                for (int tj = 0; tj < kbt; ++tj) n[TC_OZ_LOWER] += (tj * 64 <= ti * 128 + 127);
+        }
     }
+}
+size_t tables_bytes(const size_t (&n)[TC_COUNT]) {
     size_t b = 0;
-    b += gapro_align_up(rs.size() * sizeof(Region), 256);
-    b += gapro_align_up(full * 16, 256) + gapro_align_up(lower * 16, 256) + gapro_align_up(wide * 16, 256);
-    b += gapro_align_up(rows * 8, 256) + gapro_align_up(rowsp * 8, 256) + gapro_align_up(panel * 8, 256);
-    b += gapro_align_up(upd * 16, 256);
-    return b + 256 + (size_t)8 * 12 * 256;   // + per-group table alignment slack (up to MAX_GROUPS = 8 side streams)
+    for (int i = 0; i < TC_COUNT; ++i) b += gapro_align_up(n[i] ? n[i] * TC_ELEM[i] : 1, 256);
+    return b;
+}
+
+// bytes of descriptors + tile tables for a set of regions that run_regions may split into up to MAX_GROUPS = 8
+// stream groups: the counts are additive over regions, every group pays its own per-table alignment
+size_t aux_bytes(const std::vector<Region>& rs) {
+    size_t n[TC_COUNT];
+    count_tables(rs, n);
+    return tables_bytes(n) + (size_t)8 * TC_COUNT * 256;
 }
 
 thread_local int64_t g_launches = 0;
@@ -1262,19 +1325,16 @@ struct ChunkTables {
     int4* upd;                      // update tiles of all block steps, step-major
     std::vector<int> upd_off;       // upd_off[kb] .. upd_off[kb+1]: tiles of step kb
     int n_full, n_lower, n_wide, n_rows, n_rowsp;
+    // the tile products of the training steps: small regions (DMMA tiles) / large regions (tcgen05, gp_ozaki.cuh)
+    int4 *full_s, *lower_s, *oz_blk, *oz_full, *oz_lower;
+    int2* oz_vb;
+    int n_full_s, n_lower_s, n_oz_vb, n_oz_blk, n_oz_full, n_oz_lower;
     std::vector<int> cnt_gt;        // cnt_gt[kb] = #regions with nb > kb
     std::vector<int> panel_prefix;  // panel tiles of the first cnt_gt[kb] regions
     int nbmax;
     int sweep_group;                // block steps whose trailing updates are applied in one pass
 };
 
-// Trailing updates of the sweep are applied `group` block steps at a time (contraction depth group * 64);
-// between two full passes only the next block column / block row is brought up to date.
-static int sweep_group_size() {
-    int g = 4;      // measured on the bench batch: 2 -> 1563 ms, 4 -> 1544 ms, 8 -> 1559 ms per step
-    if (const char* e = getenv("GAPRO_GP_SWEEP_GROUP")) g = atoi(e);
-    return g < 1 ? 1 : (g > 8 ? 8 : g);
-}
 
 
 // ---- opt-in per-phase profiling with CUDA events on the launching stream ------------------
@@ -1406,6 +1466,61 @@ struct Driver {
         return p;
     }
 
+    int ozS = 6;      // digits per operand of the tcgen05 path
+
+    void oz_slice(int mat, int flags, int buf, const GpParams& p) {
+        k_oz_vecscale_b<<<tb.n_oz_vb, 256, 0, stream>>>(tb.regs, tb.oz_vb, p, ws, ozS, mat, flags, buf);
+        if (ozS == 5) k_oz_slice_b<5><<<tb.n_oz_blk, 256, 0, stream>>>(tb.regs, tb.oz_blk, p, ws, mat, flags, buf);
+        else if (ozS == 6) k_oz_slice_b<6><<<tb.n_oz_blk, 256, 0, stream>>>(tb.regs, tb.oz_blk, p, ws, mat, flags, buf);
+        else k_oz_slice_b<7><<<tb.n_oz_blk, 256, 0, stream>>>(tb.regs, tb.oz_blk, p, ws, mat, flags, buf);
+        g_launches += 2;
+    }
+    template <int PH>
+    void oz_gemm(bool lower, int abuf, int bbuf, const GpParams& p) {
+        const int4* tiles = lower ? tb.oz_lower : tb.oz_full;
+        const int n = lower ? tb.n_oz_lower : tb.n_oz_full;
+        if (ozS == 5) k_oz_gemm_b<5, PH><<<n, oz::OZ_THREADS, oz::oz_smem_bytes(5), stream>>>(tb.regs, tiles, p, ws, abuf, bbuf);
+        else if (ozS == 6) k_oz_gemm_b<6, PH><<<n, oz::OZ_THREADS, oz::oz_smem_bytes(6), stream>>>(tb.regs, tiles, p, ws, abuf, bbuf);
+        else k_oz_gemm_b<7, PH><<<n, oz::OZ_THREADS, oz::oz_smem_bytes(7), stream>>>(tb.regs, tiles, p, ws, abuf, bbuf);
+        ++g_launches;
+    }
+    // phase PH of the large regions: slice the operands it contracts, then the tcgen05 tile product
+    template <int PH>
+    void oz_phase(const GpParams& p) {
+        if (tb.n_oz_vb <= 0) return;
+        if (PH == PH_A) {            // A = L^-1 K_zx
+            oz_slice(OM_LINV, 0, OB_LR, p);
+            oz_slice(OM_LINV, OZF_TRANS, OB_LC, p);      // columns of L^-1: G_C, Y, G_K
+            oz_slice(OM_KZX, OZF_TRANS, OB_X1, p);
+            oz_gemm<PH_A>(false, OB_LR, OB_X1, p);
+        } else if (PH == PH_B) {     // B = T^T A
+            oz_slice(OM_T, OZF_TRANS, OB_X2, p);
+            oz_slice(OM_A, OZF_TRANS, OB_X3, p);
+            oz_gemm<PH_B>(false, OB_X2, OB_X3, p);
+        } else if (PH == PH_GA) {    // T B
+            oz_slice(OM_T, 0, OB_X1, p);
+            oz_slice(OM_BM, OZF_TRANS, OB_X2, p);
+            oz_gemm<PH_GA>(false, OB_X1, OB_X2, p);
+        } else if (PH == PH_GT) {    // A diag(g_v) B^T
+            oz_slice(OM_A, OZF_GV, OB_X1, p);
+            oz_slice(OM_BM, 0, OB_X2, p);
+            oz_gemm<PH_GT>(true, OB_X1, OB_X2, p);
+        } else if (PH == PH_GC) {    // L^-T G_A
+            oz_slice(OM_GA, OZF_TRANS, OB_X1, p);
+            oz_gemm<PH_GC>(false, OB_LC, OB_X1, p);
+        } else if (PH == PH_GL) {    // G_A A^T
+            oz_slice(OM_GA, 0, OB_X1, p);
+            oz_slice(OM_A, 0, OB_X2, p);
+            oz_gemm<PH_GL>(true, OB_X1, OB_X2, p);
+        } else if (PH == PH_Y) {     // S L^-1   (S in the B buffer)
+            oz_slice(OM_BM, 0, OB_X1, p);
+            oz_gemm<PH_Y>(true, OB_X1, OB_LC, p);
+        } else if (PH == PH_GK) {    // L^-T Y   (Y in the G_A buffer, lower tiles only)
+            oz_slice(OM_GA, OZF_TRANS | OZF_YTRI, OB_X1, p);
+            oz_gemm<PH_GK>(true, OB_LC, OB_X1, p);
+        }
+    }
+
     template <int PH>
     void gemm(const int4* tiles, int n, const GpParams& p) {
         if (n <= 0) return;
@@ -1472,17 +1587,17 @@ struct Driver {
             PHASE(cholesky(p))
         }
         to_lo();
-        PHASE(gemm<PH_A>(tb.full, tb.n_full, p))
-        PHASE(gemm<PH_B>(tb.full, tb.n_full, p))
+        PHASE((gemm<PH_A>(tb.full_s, tb.n_full_s, p), oz_phase<PH_A>(p)))
+        PHASE((gemm<PH_B>(tb.full_s, tb.n_full_s, p), oz_phase<PH_B>(p)))
         PHASE((k_colstats<<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws, po), ++g_launches))
-        PHASE(gemm<PH_GA>(tb.full, tb.n_full, p))
-        PHASE(gemm<PH_GT>(tb.lower, tb.n_lower, p))
+        PHASE((gemm<PH_GA>(tb.full_s, tb.n_full_s, p), oz_phase<PH_GA>(p)))
+        PHASE((gemm<PH_GT>(tb.lower_s, tb.n_lower_s, p), oz_phase<PH_GT>(p)))
         PHASE((k_grad_m<<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws), ++g_launches))
-        PHASE(gemm<PH_GC>(tb.full, tb.n_full, p))
-        PHASE(gemm<PH_GL>(tb.lower, tb.n_lower, p))
+        PHASE((gemm<PH_GC>(tb.full_s, tb.n_full_s, p), oz_phase<PH_GC>(p)))
+        PHASE((gemm<PH_GL>(tb.lower_s, tb.n_lower_s, p), oz_phase<PH_GL>(p)))
         PHASE((void)0)   // (slot of the former L^T G_L product, folded into the previous phase)
-        PHASE(gemm<PH_Y>(tb.lower, tb.n_lower, p))   // G_K's lower tiles read only Y[k >= j]
-        PHASE(gemm<PH_GK>(tb.lower, tb.n_lower, p))
+        PHASE((gemm<PH_Y>(tb.lower_s, tb.n_lower_s, p), oz_phase<PH_Y>(p)))   // G_K's lower tiles read only Y[k >= j]
+        PHASE((gemm<PH_GK>(tb.lower_s, tb.n_lower_s, p), oz_phase<PH_GK>(p)))
         PHASE(kgrad(p))
         PHASE((k_adam_small<<<n_regs, 256, 0, stream>>>(tb.regs, p, ws), ++g_launches))
 #undef PHASE
@@ -1513,8 +1628,8 @@ struct Driver {
 // lays out one chunk (regions already carry .base), uploads descriptors and tile tables
 int setup_chunk(std::vector<Region>& rs, char* aux, const char* aux_end, cudaStream_t stream, ChunkTables& tb,
                 size_t* consumed) {
-    std::vector<int4> full, lower, wide;
-    std::vector<int2> rows, rowsp, panel;
+    std::vector<int4> full, lower, wide, full_s, lower_s, oz_blk, oz_full, oz_lower;
+    std::vector<int2> rows, rowsp, panel, oz_vb;
     tb.nbmax = 0;
     for (size_t r = 0; r < rs.size(); ++r) tb.nbmax = std::max(tb.nbmax, rs[r].nb);
     tb.cnt_gt.assign(tb.nbmax + 1, 0);
@@ -1527,6 +1642,21 @@ int setup_chunk(std::vector<Region>& rs, char* aux, const char* aux_end, cudaStr
             for (int tj = 0; tj <= ti; ++tj) lower.push_back(make_int4((int)r, ti, tj, 0));
             for (int tj = 0; tj < R.nbw; ++tj) wide.push_back(make_int4((int)r, ti, tj, 0));
             rows.push_back(make_int2((int)r, ti));
+            if (!R.oz) {
+                for (int tj = 0; tj < R.nb; ++tj) full_s.push_back(make_int4((int)r, ti, tj, 0));
+                for (int tj = 0; tj <= ti; ++tj) lower_s.push_back(make_int4((int)r, ti, tj, 0));
+            }
+        }
+        if (R.oz) {
+            const int kbt = (R.M + 63) / 64, t128 = (R.M + 127) / 128;
+            for (int vb = 0; vb < kbt; ++vb) oz_vb.push_back(make_int2((int)r, vb));
+            for (int kb = 0; kb < kbt; ++kb)
+                for (int rb = 0; rb < kbt; ++rb) oz_blk.push_back(make_int4((int)r, kb, rb, 0));
+            for (int ti = 0; ti < t128; ++ti)
+                for (int tj = 0; tj < kbt; ++tj) {
+                    oz_full.push_back(make_int4((int)r, ti, tj, 0));
+                    if (tj * 64 <= ti * 128 + 127) oz_lower.push_back(make_int4((int)r, ti, tj, 0));
+                }
         }
         for (int t = 0; t < R.Np / TB; ++t)
             if (t * TB < R.N) rowsp.push_back(make_int2((int)r, t));
@@ -1558,12 +1688,19 @@ int setup_chunk(std::vector<Region>& rs, char* aux, const char* aux_end, cudaStr
     }
     tb.upd_off[tb.nbmax] = (int)upd.size();
     // table bytes of this group before anything is copied: the chunk was sized with aux_bytes(chunk), which
-    // covers the tables of all its groups plus ONE alignment slack term
+    // covers the tables of all its groups and their per-table alignment
     {
-        const size_t sizes[8] = {rs.size() * sizeof(Region), full.size() * 16, lower.size() * 16, wide.size() * 16,
-                                 rows.size() * 8, rowsp.size() * 8, panel.size() * 8, upd.size() * 16};
-        size_t need = 0;
-        for (size_t b : sizes) need += gapro_align_up(b ? b : 1, 256);
+        size_t n[TC_COUNT];
+        count_tables(rs, n);
+        const size_t need = tables_bytes(n);
+        const size_t have[TC_COUNT] = {rs.size(), full.size(), lower.size(), wide.size(), rows.size(), rowsp.size(),
+                                       panel.size(), upd.size(), full_s.size(), lower_s.size(), oz_vb.size(),
+                                       oz_blk.size(), oz_full.size(), oz_lower.size()};
+        for (int i = 0; i < TC_COUNT; ++i)
+            if (have[i] != n[i]) {
+                gapro_set_error("gapro_gp_fit_batch: tile table %d has %zu entries, the layout counted %zu", i, have[i], n[i]);
+                return GAPRO_ERR_WORKSPACE;
+            }
         if (aux + need > aux_end) {
             gapro_set_error("gapro_gp_fit_batch: tile tables (%zu bytes) overrun the workspace by %zu bytes", need,
                             (size_t)(aux + need - aux_end));
@@ -1585,6 +1722,18 @@ int setup_chunk(std::vector<Region>& rs, char* aux, const char* aux_end, cudaStr
     tb.rowsp = (int2*)put(rowsp.data(), rowsp.size() * 8);
     tb.panel = (int2*)put(panel.data(), panel.size() * 8);
     tb.upd = (int4*)put(upd.data(), upd.size() * 16);
+    tb.full_s = (int4*)put(full_s.data(), full_s.size() * 16);
+    tb.lower_s = (int4*)put(lower_s.data(), lower_s.size() * 16);
+    tb.oz_vb = (int2*)put(oz_vb.data(), oz_vb.size() * 8);
+    tb.oz_blk = (int4*)put(oz_blk.data(), oz_blk.size() * 16);
+    tb.oz_full = (int4*)put(oz_full.data(), oz_full.size() * 16);
+    tb.oz_lower = (int4*)put(oz_lower.data(), oz_lower.size() * 16);
+    tb.n_full_s = (int)full_s.size();
+    tb.n_lower_s = (int)lower_s.size();
+    tb.n_oz_vb = (int)oz_vb.size();
+    tb.n_oz_blk = (int)oz_blk.size();
+    tb.n_oz_full = (int)oz_full.size();
+    tb.n_oz_lower = (int)oz_lower.size();
     *consumed = o;
     tb.n_full = (int)full.size();
     tb.n_lower = (int)lower.size();
@@ -1650,29 +1799,12 @@ extern "C" int64_t gapro_gp_debug_aux_slack(int32_t n_regions, const int32_t* tr
     std::vector<Region> rs = sorted_regions(n_regions, train_off, nullptr, test_off);
     std::vector<std::vector<Region>> gs(groups);
     for (size_t i = 0; i < rs.size(); ++i) gs[i % groups].push_back(rs[i]);
-    const int sg = sweep_group_size();
     int64_t used = 0;
     for (const std::vector<Region>& g : gs) {
         if (g.empty()) continue;
-        size_t full = 0, lower = 0, wide = 0, rows = 0, rowsp = 0, panel = 0, upd = 0;
-        for (const Region& r : g) {
-            full += (size_t)r.nb * r.nb;
-            lower += (size_t)r.nb * (r.nb + 1) / 2;
-            wide += (size_t)r.nb * r.nbw;
-            rows += r.nb;
-            for (int t = 0; t < r.Np / TB; ++t) rowsp += (t * TB < r.N);
-            panel += r.nb - 1;
-            for (int kb = 0; kb < r.nb; ++kb) {
-                if (kb % sg == sg - 1) {
-                    for (int i = r.nb - 1; i > kb; --i) upd += i + 1;
-                } else if (kb + 1 < r.nb) {
-                    upd += (r.nb - 1 - kb) + (kb + 1);
-                }
-            }
-        }
-        const size_t sizes[8] = {g.size() * sizeof(Region), full * 16, lower * 16, wide * 16, rows * 8, rowsp * 8,
-                                 panel * 8, upd * 16};
-        for (size_t b : sizes) used += (int64_t)gapro_align_up(b ? b : 1, 256);
+        size_t n[TC_COUNT];
+        count_tables(g, n);
+        used += (int64_t)tables_bytes(n);
     }
     return (int64_t)aux_bytes(rs) - used;
 }
@@ -1757,6 +1889,23 @@ static int set_kernel_attributes() {
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GL>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_Y>, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_GK>, GEMM_SMEM);
+#define OZ_ATTR(S_)                                                                                     \
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_gemm_b<S_, PH_A>, oz::oz_smem_bytes(S_));                  \
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_gemm_b<S_, PH_B>, oz::oz_smem_bytes(S_));                  \
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_gemm_b<S_, PH_GA>, oz::oz_smem_bytes(S_));                 \
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_gemm_b<S_, PH_GT>, oz::oz_smem_bytes(S_));                 \
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_gemm_b<S_, PH_GC>, oz::oz_smem_bytes(S_));                 \
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_gemm_b<S_, PH_GL>, oz::oz_smem_bytes(S_));                 \
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_gemm_b<S_, PH_Y>, oz::oz_smem_bytes(S_));                  \
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_gemm_b<S_, PH_GK>, oz::oz_smem_bytes(S_));
+    OZ_ATTR(5)
+    OZ_ATTR(6)
+    OZ_ATTR(7)
+#undef OZ_ATTR
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_vecscale_b, 0);
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_slice_b<5>, 0);
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_slice_b<6>, 0);
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_slice_b<7>, 0);
     if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<6, 4>, kgrad_smem<6, 4>());
     if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<8, 4>, kgrad_smem<8, 4>());
     if (!getenv("GAPRO_GP_DEFAULT_CARVEOUT")) {
@@ -1788,6 +1937,7 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
         while (pos + chunk.size() < all.size()) {
             Region r = all[pos + chunk.size()];
             r.base = (long long)doubles;
+            r.oz_base = (long long)(doubles + region_core_doubles(r, D));
             chunk.push_back(r);
             size_t nd = doubles + region_doubles(r, D);
             if (nd * 8 + aux_bytes(chunk) > ws_bytes) {
@@ -1821,6 +1971,7 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
                 d.stream = d.s_hi;
                 if (g > 0 && !getenv("GAPRO_GP_NO_STAGGER")) d.ev_prev_swept = g_pool.swept[g - 1];
             }
+            d.ozS = oz_digits();
             d.careful = careful;
             if (careful) d.tb_orig = groups[g][0].orig;
             d.D = D;
