@@ -57,6 +57,8 @@ _SIGNATURES = {
     "gapro_ozaki_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "gapro_ozaki_gemm": (ctypes.c_int, [P, c_int32, c_int32, P, P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                         P, c_int32, P, c_size_t, c_int32, P, P, P]),
+    "gapro_instance_info_workspace_bytes": (c_size_t, [c_int32]),
+    "gapro_instance_info": (ctypes.c_int, [P, P, P, c_int64, c_int32, c_int32, P, P, P, P, P, c_size_t, P]),
     "gapro_eval_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "gapro_eval_miou_scene": (ctypes.c_int, [P, P, P, P, c_int64, c_int32, c_int32, P, P, P, c_size_t, P]),
     "gapro_eval_sem_conf": (ctypes.c_int, [P, P, c_int64, c_int32, P, P]),

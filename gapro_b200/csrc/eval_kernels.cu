@@ -154,3 +154,127 @@ extern "C" int gapro_eval_sem_conf(const int32_t* gt_sem, const int32_t* ps_sem,
     GAPRO_KERNEL_CHECK();
     return GAPRO_OK;
 }
+
+// =============================================================================================
+// G - per-instance axis-aligned boxes on the device: getInstanceInfo (gen_ps_utils.py:195-239).
+// The reference loops over instance ids with np.where; here ONE pass over the points keeps, per id, the
+// min / max of xyz (exact: ordered-uint64 atomics, order-free) and the index of the first point (its semantic
+// label is the class, :212-213); a second tiny kernel lists the ids in use in increasing order (:209-210 skips
+// empty ids), writes the float64 boxes, the volumes prod(clip(max - min, 0)) (:227) and the classes
+// (scannetv2: minus 2 unless -100, :236-237).
+// =============================================================================================
+namespace {
+
+__device__ __forceinline__ unsigned long long gi_key(double d) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double gi_dbl(unsigned long long u) {
+    unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void k_gi_init(unsigned long long* __restrict__ ext, int32_t* __restrict__ first, int n_ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_ids * 6) ext[i] = (i % 6) < 3 ? ~0ull : 0ull;
+    if (i < n_ids) first[i] = INT32_MAX;
+}
+
+__global__ void __launch_bounds__(256)
+k_gi_points(const double* __restrict__ xyz, const double* __restrict__ inst, int64_t n, int n_ids,
+            unsigned long long* __restrict__ ext, int32_t* __restrict__ first) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+        const double v = inst[p];
+        if (!(v >= 0.0) || v != floor(v) || v >= (double)n_ids) continue;      // np.where(instance_label == i), i >= 0
+        const int id = (int)v;
+        const double x = xyz[3 * p], y = xyz[3 * p + 1], z = xyz[3 * p + 2];
+        unsigned long long* e = ext + (size_t)id * 6;
+        atomicMin(e + 0, gi_key(x));
+        atomicMin(e + 1, gi_key(y));
+        atomicMin(e + 2, gi_key(z));
+        atomicMax(e + 3, gi_key(x));
+        atomicMax(e + 4, gi_key(y));
+        atomicMax(e + 5, gi_key(z));
+        atomicMin(first + id, (int32_t)p);
+    }
+}
+
+// one CTA: ids in use in increasing order
+__global__ void __launch_bounds__(1024)
+k_gi_finish(const unsigned long long* __restrict__ ext, const int32_t* __restrict__ first, const double* __restrict__ sem,
+            int n_ids, int scannet, double* __restrict__ boxes, double* __restrict__ vol, double* __restrict__ cls,
+            int32_t* __restrict__ n_used) {
+    __shared__ int s_cnt[1024];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n_ids; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const int used = (i < n_ids && first[i] != INT32_MAX) ? 1 : 0;
+        s_cnt[threadIdx.x] = used;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {                 // inclusive scan
+            const int v = threadIdx.x >= o ? s_cnt[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_cnt[threadIdx.x] += v;
+            __syncthreads();
+        }
+        if (used) {
+            const int k = s_base + s_cnt[threadIdx.x] - 1;
+            double lo[3], hi[3];
+            double v = 1.0;
+            for (int d = 0; d < 3; ++d) {
+                lo[d] = gi_dbl(ext[(size_t)i * 6 + d]);
+                hi[d] = gi_dbl(ext[(size_t)i * 6 + 3 + d]);
+                boxes[6 * k + d] = lo[d];
+                boxes[6 * k + 3 + d] = hi[d];
+            }
+            for (int d = 0; d < 3; ++d) {
+                double e = __dsub_rn(hi[d], lo[d]);
+                e = e < 0.0 ? 0.0 : e;
+                v = d == 0 ? e : __dmul_rn(v, e);
+            }
+            vol[k] = v;
+            double c = sem[first[i]];
+            if (scannet && c != -100.0) c -= 2.0;
+            cls[k] = c;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_base += s_cnt[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_used = s_base;
+}
+
+}  // namespace
+
+extern "C" size_t gapro_instance_info_workspace_bytes(int32_t n_ids) {
+    if (n_ids <= 0) return 0;
+    return gapro_align_up((size_t)n_ids * 6 * 8, 256) + gapro_align_up((size_t)n_ids * 4, 256);
+}
+
+extern "C" int gapro_instance_info(const double* xyz, const double* instance_label, const double* semantic_label,
+                                   int64_t n_points, int32_t n_ids, int32_t scannet, double* boxes, double* volumes,
+                                   double* classes, int32_t* n_used_dev, void* ws, size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GAPRO_REQUIRE(xyz && instance_label && semantic_label && boxes && volumes && classes && n_used_dev && ws,
+                  "gapro_instance_info: null pointer");
+    GAPRO_REQUIRE(n_points > 0 && n_points < (int64_t)INT32_MAX && n_ids > 0, "gapro_instance_info: bad sizes");
+    if (ws_bytes < gapro_instance_info_workspace_bytes(n_ids)) {
+        gapro_set_error("gapro_instance_info: workspace %zu < %zu bytes", ws_bytes, gapro_instance_info_workspace_bytes(n_ids));
+        return GAPRO_ERR_WORKSPACE;
+    }
+    unsigned long long* ext = (unsigned long long*)ws;
+    int32_t* first = (int32_t*)((char*)ws + gapro_align_up((size_t)n_ids * 6 * 8, 256));
+    k_gi_init<<<(n_ids * 6 + 255) / 256, 256, 0, stream>>>(ext, first, n_ids);
+    int dev = 0, sms = 148;
+    GAPRO_CUDA_TRY(cudaGetDevice(&dev));
+    GAPRO_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t want = (n_points + 255) / 256;
+    const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    k_gi_points<<<grid, 256, 0, stream>>>(xyz, instance_label, n_points, n_ids, ext, first);
+    k_gi_finish<<<1, 1024, 0, stream>>>(ext, first, semantic_label, n_ids, scannet, boxes, volumes, classes, n_used_dev);
+    GAPRO_KERNEL_CHECK();
+    return GAPRO_OK;
+}

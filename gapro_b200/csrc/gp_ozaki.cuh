@@ -234,15 +234,23 @@ k_oz_gemm_b(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpP
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = 0.0;
             if (nkb > 0) {
-                int32_t v[S][16];
+                // the S accumulators in two batches (register budget), smallest weights first
 #pragma unroll
-                for (int g = 0; g < S; ++g) tc_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(g * OZ_BN + 16 * c), v[g]);
-                tc_wait_ld();
+                for (int h = (S - 1) / 4; h >= 0; --h) {
+                    int32_t v[4][16];
 #pragma unroll
-                for (int g = S - 1; g >= 0; --g) {
-                    const double w = __longlong_as_double((long long)(1023 - (12 + 7 * g)) << 52);      // 2^-(12+7g)
+                    for (int g = 0; g < 4; ++g)
+                        if (4 * h + g < S)
+                            tc_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)((4 * h + g) * OZ_BN + 16 * c), v[g]);
+                    tc_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = fma((double)v[g][j], w, acc[j]);
+                    for (int g = 3; g >= 0; --g) {
+                        if (4 * h + g < S) {
+                            const double w = __longlong_as_double((long long)(1023 - (12 + 7 * (4 * h + g))) << 52);   // 2^-(12+7g)
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) acc[j] = fma((double)v[g][j], w, acc[j]);
+                        }
+                    }
                 }
             }
             const int gc0 = tj * OZ_BN + 16 * c;

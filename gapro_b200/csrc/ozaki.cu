@@ -130,16 +130,23 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_gemm(OzGemm P) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] = 0.0;
             if (nkb > 0) {
-                int32_t v[S][16];
+                // the S accumulators in two batches (register budget), smallest weights first
 #pragma unroll
-                for (int g = 0; g < S; ++g) tc_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(g * OZ_BN + 16 * c), v[g]);
-                tc_wait_ld();
-                // smallest weights first
+                for (int h = (S - 1) / 4; h >= 0; --h) {
+                    int32_t v[4][16];
 #pragma unroll
-                for (int g = S - 1; g >= 0; --g) {
-                    const double w = __longlong_as_double((long long)(1023 - (12 + 7 * g)) << 52);      // 2^-(12+7g)
+                    for (int g = 0; g < 4; ++g)
+                        if (4 * h + g < S)
+                            tc_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)((4 * h + g) * OZ_BN + 16 * c), v[g]);
+                    tc_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = fma((double)v[g][j], w, acc[j]);
+                    for (int g = 3; g >= 0; --g) {
+                        if (4 * h + g < S) {
+                            const double w = __longlong_as_double((long long)(1023 - (12 + 7 * (4 * h + g))) << 52);   // 2^-(12+7g)
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) acc[j] = fma((double)v[g][j], w, acc[j]);
+                        }
+                    }
                 }
             }
             if (gr < P.M) {
@@ -252,7 +259,7 @@ int oz_run(const double* A, int lda, int transA, const double* ks, const double*
     uint8_t* bp = (uint8_t*)ws + L.b_planes;
     double* sa = (double*)((char*)ws + L.sa);
     double* sb = (double*)((char*)ws + L.sb);
-    static bool attr_done[64] = {};
+    static bool attr_done[64] = {};      // (one flag per template instantiation and device)
     int dev = 0;
     GAPRO_CUDA_TRY(cudaGetDevice(&dev));
     if (!attr_done[dev & 63]) {
@@ -315,6 +322,7 @@ extern "C" int gapro_ozaki_gemm(const double* A, int32_t lda, int32_t transA, co
         case 4: return oz_run<4>(A, lda, transA, kscale, B, ldb, transB, M, N, K, C, ldc, ws, L, reps, ms_slice, ms_gemm, stream);
         case 5: return oz_run<5>(A, lda, transA, kscale, B, ldb, transB, M, N, K, C, ldc, ws, L, reps, ms_slice, ms_gemm, stream);
         case 6: return oz_run<6>(A, lda, transA, kscale, B, ldb, transB, M, N, K, C, ldc, ws, L, reps, ms_slice, ms_gemm, stream);
-        default: return oz_run<7>(A, lda, transA, kscale, B, ldb, transB, M, N, K, C, ldc, ws, L, reps, ms_slice, ms_gemm, stream);
+        case 7: return oz_run<7>(A, lda, transA, kscale, B, ldb, transB, M, N, K, C, ldc, ws, L, reps, ms_slice, ms_gemm, stream);
+        default: return oz_run<8>(A, lda, transA, kscale, B, ldb, transB, M, N, K, C, ldc, ws, L, reps, ms_slice, ms_gemm, stream);
     }
 }

@@ -7,7 +7,7 @@
 
 namespace oz {
 
-constexpr int OZ_MAXS = 7;
+constexpr int OZ_MAXS = 8;      // 8 accumulators of 64 columns = the 512 TMEM columns of an SM
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 64;
 constexpr int OZ_BLK = 64 * 64;                 // bytes of one (64 vectors x 64 k) block of a digit plane
 constexpr int OZ_THREADS = 192;

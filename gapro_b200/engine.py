@@ -93,6 +93,22 @@ class GaproEngine:
             self._ws[key] = buf
         return buf
 
+    def _to_host(self, tensors):
+        """Device -> host for the few KB the host state machine needs: async copies into persistent pinned buffers,
+        ONE synchronisation for all of them (a plain `.cpu()` per tensor is a blocking copy each)."""
+        out = []
+        for i, t in enumerate(tensors):
+            key = ("host", i, t.dtype)
+            buf = self._ws.get(key)
+            if buf is None or buf.numel() < t.numel():
+                buf = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
+                self._ws[key] = buf
+            view = buf[:t.numel()].view(t.shape)
+            view.copy_(t, non_blocking=True)
+            out.append(view)
+        torch.cuda.current_stream(self.device).synchronize()
+        return [v.numpy().copy() for v in out]
+
     def _dev(self, arr: np.ndarray) -> torch.Tensor:
         return torch.from_numpy(np.ascontiguousarray(arr)).to(self.device, non_blocking=False)
 
@@ -221,9 +237,7 @@ class GaproEngine:
             return None
 
         # ---- P: pair state machine on the host --------------------------------------------
-        boxes_h = boxes.cpu().numpy()
-        excl_h = excl_cnt.cpu().numpy()
-        inter_h = inter_cnt.cpu().numpy()
+        boxes_h, excl_h, inter_h = self._to_host([boxes, excl_cnt, inter_cnt])
         ev = plan.enumerate_events(boxes_h, excl_h, inter_h, box_off, stride)
         pl = plan.plan_lists(ev, box_off, excl_h, inter_h)
         ev_off, ev_scene, ev_kind, ev_b1, ev_b2 = ev["ev_off"], ev["ev_scene"], ev["ev_kind"], ev["ev_b1"], ev["ev_b2"]

@@ -14,7 +14,7 @@ from . import _lib
 from .engine import SceneInputs, get_engine
 
 __all__ = ["gen_pseudo_label_gaussian_process", "gen_pseudo_labels_batch", "gen_pseudo_label_box2mask",
-           "gen_pseudo_label", "getInstanceInfo", "batch_giou_cross", "is_box1_in_box2", "is_within_bb_torch",
+           "gen_pseudo_label", "getInstanceInfo", "getInstanceInfo_cuda", "batch_giou_cross", "is_box1_in_box2", "is_within_bb_torch",
            "SceneInputs"]
 
 
@@ -136,6 +136,39 @@ def getInstanceInfo(xyz, instance_label, semantic_label, dataset_name="scannetv2
     if dataset_name == "scannetv2":
         instance_cls[instance_cls != -100] -= 2
     return instance_num, instance_cls, instance_box, instance_box_volume, corners_label
+
+
+def getInstanceInfo_cuda(xyz, instance_label, semantic_label, dataset_name="scannetv2"):
+    """getInstanceInfo on the device (gapro_instance_info): same instance order, boxes, classes and volumes as
+    the host version (bit for bit: min / max are exact and the volume is the same float64 product), from CUDA
+    tensors xyz (N,3) float64, instance_label / semantic_label (N,) float64.  Returns
+    (instance_num, instance_cls (K,) float64, instance_box (K,6) float64, instance_box_volume (K,) float64) as
+    device tensors, or None when no instance is labelled (gen_ps_utils.py:229-230).  `corners_label` - never read by
+    gen_ps.py - is not produced."""
+    if not xyz.is_cuda:
+        raise _lib.GaproError("getInstanceInfo_cuda needs CUDA tensors; use getInstanceInfo on the host")
+    lib = _lib.load()
+    dev = xyz.device
+    xyz = xyz.to(torch.float64).contiguous()
+    inst = instance_label.to(dev, torch.float64).contiguous()
+    sem = semantic_label.to(dev, torch.float64).contiguous()
+    n_ids = int(inst.max().item()) + 1
+    if n_ids <= 0:
+        return None
+    boxes = torch.empty((n_ids, 6), dtype=torch.float64, device=dev)
+    vol = torch.empty(n_ids, dtype=torch.float64, device=dev)
+    cls = torch.empty(n_ids, dtype=torch.float64, device=dev)
+    n_used = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(lib.gapro_instance_info_workspace_bytes(n_ids), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.gapro_instance_info(xyz.data_ptr(), inst.data_ptr(), sem.data_ptr(), xyz.shape[0], n_ids,
+                                           1 if dataset_name == "scannetv2" else 0, boxes.data_ptr(), vol.data_ptr(),
+                                           cls.data_ptr(), n_used.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           torch.cuda.current_stream(dev).cuda_stream), "gapro_instance_info")
+    k = int(n_used.item())
+    if k == 0:
+        return None
+    return n_ids, cls[:k], boxes[:k], vol[:k]
 
 
 def batch_giou_cross(boxes1, boxes2):

@@ -344,6 +344,20 @@ int gapro_eval_miou_scene(const int32_t* gt_sem, const int32_t* gt_inst, const i
 int gapro_eval_sem_conf(const int32_t* gt_sem, const int32_t* ps_sem, int64_t n_points, int32_t num_classes,
                         int64_t* conf, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * G - boxes from labelled points on the device.  Replaces getInstanceInfo (gen_ps_utils.py:195-239) for the
+ * values gen_ps.py uses (:72-74): instances in increasing ground-truth id with unused ids skipped (:209-210),
+ * per instance min / max of the (axis-aligned) xyz in float64, class = semantic label of its first point
+ * (minus 2 for scannetv2 unless -100, :236-237), volume = prod(clip(max - min, 0)) (:227).
+ *   instance_label / semantic_label dev double[n_points] as loaded from the scene file; n_ids = max id + 1;
+ *   boxes dev double[n_ids, 6], volumes / classes dev double[n_ids] - the first *n_used_dev rows are filled.
+ *   (`corners_label`, which gen_ps.py never reads, is not produced.)
+ */
+size_t gapro_instance_info_workspace_bytes(int32_t n_ids);
+int gapro_instance_info(const double* xyz, const double* instance_label, const double* semantic_label,
+                        int64_t n_points, int32_t n_ids, int32_t scannet, double* boxes, double* volumes,
+                        double* classes, int32_t* n_used_dev, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,8 @@ def run(case_id, M, D, N, mu_ref, var_ref, label):
     dev = torch.device("cuda:0")
     X, n1, Xt, noise = gp_case(case_id, M, D, N)
     feats = torch.from_numpy(np.concatenate([X, Xt])).to(dev)
-    for env in ({"GAPRO_GP_OZAKI": "0"}, {"GAPRO_GP_OZAKI_S": "5"}, {"GAPRO_GP_OZAKI_S": "6"}, {"GAPRO_GP_OZAKI_S": "7"}):
+    for env in ({"GAPRO_GP_OZAKI": "0"}, {"GAPRO_GP_OZAKI": "1", "GAPRO_GP_OZAKI_S": "6"},
+                {"GAPRO_GP_OZAKI": "1", "GAPRO_GP_OZAKI_S": "7"}, {"GAPRO_GP_OZAKI": "1", "GAPRO_GP_OZAKI_S": "8"}):
         for k in ("GAPRO_GP_OZAKI", "GAPRO_GP_OZAKI_S", "GAPRO_GP_OZAKI_MIN_M"):
             os.environ.pop(k, None)
         os.environ.update(env)

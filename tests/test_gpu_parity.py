@@ -625,3 +625,74 @@ def test_eval_kernels_match_reference_run(dev, lib):
         assert np.allclose(got.cpu().numpy(), ref[f"{name}_miou"], rtol=0, atol=1e-6)
     conf = get_scene_sem_conf(torch.from_numpy(ref["conf_gt"]).to(dev), torch.from_numpy(ref["conf_ps"]).to(dev))
     assert conf.is_cuda and np.array_equal(conf.cpu().numpy(), ref["conf_matrix"])
+
+
+def test_instance_boxes_on_the_device_equal_host_getInstanceInfo(dev, lib):
+    """getInstanceInfo (gen_ps_utils.py:195-239) as a CUDA pass - bit-exact boxes, volumes, classes
+    and instance order against the host mirror (itself pinned to the reference run), ids with gaps, both datasets."""
+    from gapro_b200.gen_ps_utils import getInstanceInfo, getInstanceInfo_cuda
+    for name, seed in (("tiny", 3), ("small", 4), ("c1", 1000)):
+        scene = synthetic.make_scene(seed, name)
+        inp = synthetic_inputs(scene)
+        for ds in ("scannetv2", "s3dis"):
+            want = getInstanceInfo(inp["xyz"], instance_label=scene.inst.copy(), semantic_label=scene.sem.copy(), dataset_name=ds)
+            got = getInstanceInfo_cuda(torch.from_numpy(inp["xyz"]).to(dev), torch.from_numpy(scene.inst).to(dev),
+                                       torch.from_numpy(scene.sem).to(dev), dataset_name=ds)
+            assert got[0] == want[0]
+            assert np.array_equal(got[1].cpu().numpy(), np.asarray(want[1], dtype=np.float64))
+            assert np.array_equal(got[2].cpu().numpy(), want[2]) and np.array_equal(got[3].cpu().numpy(), want[3])
+    none = getInstanceInfo_cuda(torch.zeros((5, 3), dtype=torch.float64, device=dev), torch.full((5,), -100.0, device=dev),
+                                torch.zeros(5, device=dev))
+    assert none is None
+
+
+# ------------------------------------------------------------------ tcgen05 digit-plane products (opt-in path)
+def test_tcgen05_digit_plane_product_matches_float64(dev, lib):
+    """csrc/ozaki.cu: C = op(A) op(B)^T from int8 digit planes on tcgen05 (kind::i8, TMEM accumulators) against
+    torch float64, ragged sizes, both operand orientations, the k-scaled variant, 6 and 8 digits.  The error is
+    measured against the scheme's own bound: row-max x column-max x K."""
+    from tests.oz_probe import oz_gemm
+    g = torch.Generator(device=dev).manual_seed(1)
+    for (M, N, K, tA, tB) in [(128, 64, 64, 0, 0), (1, 1, 1, 0, 0), (200, 130, 100, 1, 0), (520, 333, 1000, 0, 1),
+                              (777, 1025, 640, 1, 1)]:
+        A = torch.randn((K, M) if tA else (M, K), generator=g, dtype=torch.float64, device=dev)
+        B = torch.randn((K, N) if tB else (N, K), generator=g, dtype=torch.float64, device=dev)
+        A = A * torch.pow(10.0, torch.rand(A.shape[1], generator=g, dtype=torch.float64, device=dev) * 5 - 3)
+        opA, opB = (A.t() if tA else A), (B.t() if tB else B)
+        ref = opA @ opB.t()
+        bound = opA.abs().max(1)[0][:, None] * opB.abs().max(1)[0][None, :] * K
+        for S, tol in ((6, 2e-12), (8, 2e-15)):
+            C, _, _ = oz_gemm(lib, A, tA, B, tB, S)
+            assert float(((C - ref).abs() / bound).max()) < tol, (M, N, K, tA, tB, S)
+    A = torch.randn(300, 300, generator=g, dtype=torch.float64, device=dev)
+    B = torch.randn(300, 300, generator=g, dtype=torch.float64, device=dev)
+    ks = torch.randn(300, generator=g, dtype=torch.float64, device=dev)
+    C, _, _ = oz_gemm(lib, A, 0, B, 0, 8, ks=ks)
+    ref = (A * ks) @ B.t()
+    assert float((C - ref).abs().max() / ref.abs().max()) < 1e-13
+
+
+def test_gp_fit_with_tcgen05_products_matches_golden(dev, lib, monkeypatch):
+    """GAPRO_GP_OZAKI=1: the seven tile products of every training step of large regions run on tcgen05 (8 digits).
+    Same golden fp64-oracle vectors and the same 1e-6 bar as the default DMMA path: M = 1000 and the 8k-superpoint
+    region (M = 4200)."""
+    from gapro_b200.gaussian_process_utils import fit_gp_regions
+    from tests.golden.make_golden import GP_CASES_LARGE
+    from tests.golden.make_golden_fullsize import GP_8K
+    monkeypatch.setenv("GAPRO_GP_OZAKI", "1")
+    monkeypatch.setenv("GAPRO_GP_OZAKI_MIN_M", "512")
+    gold = np.load(os.path.join(GOLD_DIR, "gp_cases_large.npz"))
+    M, D, N = GP_CASES_LARGE[1]
+    assert M == 1000
+    X, n1, Xt, noise = gp_case(101, M, D, N)
+    feats = torch.from_numpy(np.concatenate([X, Xt])).to(dev)
+    r = fit_gp_regions(feats, [np.arange(M)], [n1], [np.arange(M, M + N)], init_noise=[noise], return_float64=True)[0]
+    assert rel_err(r[5].cpu().numpy(), gold["c1_mu64"]) < TOL and rel_err(r[6].cpu().numpy(), gold["c1_var64"]) < TOL
+    g8 = np.load(os.path.join(GOLD_DIR, "gp_case_8k.npz"))
+    i, M, D, N = GP_8K
+    X, n1, Xt, noise = gp_case(i, M, D, N)
+    feats = torch.from_numpy(np.concatenate([X, Xt])).to(dev)
+    r = fit_gp_regions(feats, [np.arange(M)], [n1], [np.arange(M, M + N)], init_noise=[noise], return_float64=True)[0]
+    assert rel_err(r[5].cpu().numpy(), g8["mu64"]) < TOL and rel_err(r[6].cpu().numpy(), g8["var64"]) < TOL
+    sure = np.abs(g8["prob"] - 0.5) > EPS
+    assert (r[2].cpu().numpy()[sure] == g8["label"][sure]).all()
