@@ -1862,13 +1862,11 @@ static int ensure_pool() {
 }
 
 static int n_groups_for(const std::vector<Region>& chunk) {
-    // default 4 (measured on the 8-scene bench batch: 1602 / 1596 / 1548 ms per step with 1 / 2 / 4 groups).  Small
-    // workloads (one scene: a few hundred tiles per phase) are bound by the ~7500 launches of four groups, not by
-    // the GPU: one group below 4096 tiles per phase, two below 16384.
+    // default 4.  Measured: 1602 / 1596 / 1548 ms per step with 1 / 2 / 4 groups on the 8-scene bench batch; one
+    // configs[1] scene (93 regions): 82.1 / 81.9 / 75.5 ms with 2000 / 3828 / 7484 launches - even the single scene
+    // is bound by the dependent chain of small kernels on the GPU, not by the host's launch rate.
     const size_t n_regions = chunk.size();
-    size_t tiles = 0;
-    for (const Region& r : chunk) tiles += (size_t)r.nb * r.nb;
-    int g = tiles < 4096 ? 1 : (tiles < 16384 ? 2 : 4);
+    int g = 4;
     if (const char* e = getenv("GAPRO_GP_STREAMS")) g = atoi(e);
     if (g < 1) g = 1;
     if (g > MAX_GROUPS) g = MAX_GROUPS;

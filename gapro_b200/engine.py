@@ -71,9 +71,12 @@ class GaproEngine:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.gp_workspace_cap = gp_workspace_bytes
         self._ws = {}
-        # "points" (default): A + A' stream the points in input order; "gather": the by-superpoint kernel of round 1
+        # "gather" (default): one warp per superpoint reads its points through the sort permutation; "points": A + A'
+        # stream the points in input order and count with integer reductions (csrc/occupancy_points.cu) - bit-identical
+        # results, measured slower on B200 (90 vs 45 us on the bench batch, 394 vs 251 us on 9.5M points), kept as an
+        # alternative and covered by the parity suite
         import os
-        self.occupancy_path = os.environ.get("GAPRO_OCCUPANCY", "points")
+        self.occupancy_path = os.environ.get("GAPRO_OCCUPANCY", "gather")
         if self.occupancy_path not in ("points", "gather"):
             raise ValueError("GAPRO_OCCUPANCY must be 'points' or 'gather'")
 
@@ -198,7 +201,7 @@ class GaproEngine:
         inter_cnt = torch.empty((ns, stride, stride), dtype=torch.int32, device=dev)
         thresh32 = float(np.float32(thresh_spp_occu))
         if self.occupancy_path == "points":
-            # point order: stream xyz + dense ids, per-scene grid of box masks, integer counts in L2
+            # point order: stream xyz + dense ids, per-scene grid of box masks, integer counts in L2 (opt-in)
             cnt_in = torch.empty((St, stride), dtype=torch.int32, device=dev)
             ows = self._workspace("occ", lib.gapro_occupancy_points_workspace_bytes(ns, words))
             _lib.check(lib.gapro_occupancy_points(xyz.data_ptr(), spp_gid.data_ptr(), seg_off.data_ptr(),
@@ -209,7 +212,7 @@ class GaproEngine:
                                                   stream), "gapro_occupancy_points")
             n_launch += 3
         else:
-            # by superpoint: gather through the sort permutation (round-1 kernel, kept for comparison)
+            # by superpoint: gather through the sort permutation
             cnt_in = torch.empty((St, stride), dtype=torch.int32, device=dev) if want_cnt_in else None
             _lib.check(lib.gapro_occupancy(xyz.data_ptr(), perm.data_ptr(), seg_off.data_ptr(), spp_off_dev.data_ptr(),
                                            box_off_dev.data_ptr(), boxes.data_ptr(), ns, St, Bt, words, MARGIN,

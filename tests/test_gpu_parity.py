@@ -47,9 +47,11 @@ def unpack_bits(bits, B):
 
 
 # ----------------------------------------------------------------------------------------- stages
+@pytest.mark.parametrize("occ_path", ["gather", "points"])
 @pytest.mark.parametrize("names", [["tiny"], ["tiny", "small", "tiny"]])
-def test_stages_bit_exact_against_oracle(engine, dev, names):
+def test_stages_bit_exact_against_oracle(engine, dev, names, occ_path, monkeypatch):
     from oracle import gen_ps_oracle as O
+    monkeypatch.setattr(engine, "occupancy_path", occ_path)
     inps = [synthetic_inputs(synthetic.make_scene(7 + i, n)) for i, n in enumerate(names)]
     scenes = [to_scene_inputs(inp, dev, noise_seed=11 + i) for i, inp in enumerate(inps)]
     outs, dbg = engine.run(scenes, thresh_spp_occu=0.999, training_iter=1, debug=True, want_cnt_in=True)
@@ -105,10 +107,12 @@ def test_stages_with_more_than_32_boxes_and_many_scenes(engine, dev):
         p0 += len(inp["xyz"])
 
 
-def test_containment_edges_and_ragged_superpoints(engine, dev):
+@pytest.mark.parametrize("occ_path", ["gather", "points"])
+def test_containment_edges_and_ragged_superpoints(engine, dev, occ_path, monkeypatch):
     """Points exactly on lo-0.005 / hi+0.005, a 1-point superpoint, a 3000-point superpoint, raw ids
     with negative values and a huge offset."""
     from oracle import gen_ps_oracle as O
+    monkeypatch.setattr(engine, "occupancy_path", occ_path)
     rng = np.random.default_rng(0)
     box = np.array([[0, 0, 0, 1, 1, 1], [0.5, 0.5, 0.5, 2, 2, 2]], np.float32)
     lo, hi = 0.0 - 0.005, 1.0 + 0.005
@@ -533,13 +537,15 @@ def test_full_size_scene_matches_offline_oracle_fixture(engine, dev, tag):
     _compare_scene(out[0], ref, float(gold["min_margin"]))
 
 
+@pytest.mark.parametrize("occ_path", ["gather", "points"])
 @pytest.mark.parametrize("name", ["c4", "c5"])
-def test_stress_configs_stages_bit_exact(engine, dev, name):
+def test_stress_configs_stages_bit_exact(engine, dev, name, occ_path, monkeypatch):
     """configs[3] (80 boxes, a region of > 5k + 2.7k superpoints) and configs[4] (1M points, 125 boxes): four
     occupancy words per superpoint; stages U, F, A, A', B, P and the region index lists bit-exact against the
     oracle.  The GP runs with training_iter = 0 (prediction only) - its arithmetic at these sizes is covered by
     the 8k-region golden test."""
     from oracle import gen_ps_oracle as O
+    monkeypatch.setattr(engine, "occupancy_path", occ_path)
     inp = synthetic_inputs(synthetic.make_scene(1000, name))
     _, od = O.gen_pseudo_label_oracle(*oracle_args(inp), thresh_spp_occu=0.999, fit_fn=fake_fit, noise_seed=3,
                                       return_debug=True)
