@@ -523,6 +523,135 @@ k_build(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParam
 constexpr int LDS_ = TB + 1;
 constexpr int DIAG_SMEM = (2 * TB * LDS_ + TB) * (int)sizeof(double);
 
+// 64x64 Cholesky factor (in place in sL) and its inverse (into sX, zero-initialised by the caller) in shared memory,
+// 128 threads; returns (on every thread of warp 0) whether a pivot was not positive.  Row stride LD doubles.
+template <int LD>
+__device__ __forceinline__ bool chol_inv_64(double* __restrict__ sL, double* __restrict__ sX, double* __restrict__ dinv) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bool bad = false;
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
+        const int c0 = 16 * p;
+        // (a) 16x16 diagonal block: warp 0, lane r (and its mirror r+16) owns row r
+        if (warp == 0) {
+            const int r = lane & 15;
+            double a[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a[k] = sL[(c0 + r) * LD + c0 + k];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                double piv = __shfl_sync(0xffffffffu, a[c], c);
+                if (!(piv > 0.0)) {
+                    bad = true;
+                    piv = 1.0;
+                }
+                const double rs = rsqrt(piv);
+                const double l = a[c] * rs;                 // lane c: piv * rsqrt(piv) = sqrt(piv)
+#pragma unroll
+                for (int cc = c + 1; cc < 16; ++cc) a[cc] = fma(-l, __shfl_sync(0xffffffffu, l, cc), a[cc]);
+                a[c] = l;
+                if (lane == c) dinv[c0 + c] = rs;
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) sL[(c0 + r) * LD + c0 + k] = (k <= r) ? a[k] : 0.0;
+            }
+        }
+        __syncthreads();
+        // (b) rows below the block: one thread per row, forward substitution against the 16x16 factor
+        const int nt = 48 - 16 * p;
+        if (tid < nt) {
+            const int r = c0 + 16 + tid;
+            double x[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) x[k] = sL[r * LD + c0 + k];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                double sum = x[c];
+#pragma unroll
+                for (int k = 0; k < c; ++k) sum = fma(-x[k], sL[(c0 + c) * LD + c0 + k], sum);
+                x[c] = sum * dinv[c0 + c];
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sL[r * LD + c0 + k] = x[k];
+        }
+        __syncthreads();
+        // (c) trailing update of the lower triangle: thread = (row, strip of columns)
+        if (nt > 0) {
+            const int nstrip = GEMM_THREADS / nt;
+            const int rr = tid % nt, strip = tid / nt;
+            if (strip < nstrip) {
+                const int r = c0 + 16 + rr;
+                double lr[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) lr[k] = sL[r * LD + c0 + k];
+                for (int cc = c0 + 16 + strip; cc <= r; cc += nstrip) {
+                    double sum = sL[r * LD + cc];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) sum = fma(-lr[k], sL[cc * LD + c0 + k], sum);
+                    sL[r * LD + cc] = sum;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- inverse.  Diagonal 16x16 blocks: warp p, lane c (and mirror) owns column c.
+    {
+        const int c0 = 16 * warp, c = lane & 15;
+        double x[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            double sum = (q == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < q; ++k) sum = fma(-sL[(c0 + q) * LD + c0 + k], x[k], sum);
+            x[q] = sum * dinv[c0 + q];
+        }
+        if (lane < 16) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) sX[(c0 + q) * LD + c0 + c] = (q >= c) ? x[q] : 0.0;
+        }
+    }
+    __syncthreads();
+    // Off-diagonal blocks by distance d = i - j:  X_ij = -X_ii * sum_{k=j..i-1} L_ik X_kj.
+    // One warp per block; lane = (row r, half h of the 16 columns).
+#pragma unroll 1
+    for (int d = 1; d < 4; ++d) {
+        if (warp < 4 - d) {
+            const int i = warp + d, j = warp;
+            const int r = lane & 15, h = lane >> 4;
+            double t[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t[q] = 0.0;
+            const double* Lrow = sL + (16 * i + r) * LD + 16 * j;            // L[i-block row r][cols of blocks j..i-1]
+            for (int kk = 0; kk < 16 * d; ++kk) {
+                const double lv = Lrow[kk];
+                const double* xr = sX + (16 * j + kk) * LD + 16 * j + 8 * h;  // X[(blocks j..i-1) row kk][block j cols]
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t[q] = fma(lv, xr[q], t[q]);
+            }
+            // stage T in the destination block, then out = -X_ii * T
+            double* Tb = sX + (16 * i) * LD + 16 * j;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) Tb[r * LD + 8 * h + q] = t[q];
+            __syncwarp();
+            double o[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = 0.0;
+            const double* Xii = sX + (16 * i + r) * LD + 16 * i;
+            for (int m = 0; m <= r; ++m) {
+                const double xv = Xii[m];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = fma(-xv, Tb[m * LD + 8 * h + q], o[q]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) Tb[r * LD + 8 * h + q] = o[q];
+        }
+        __syncthreads();
+    }
+    return bad;
+}
+
 // 64x64 factorisation + triangular inverse in shared memory, blocked by 16: the 16x16 diagonal blocks
 // are factored / inverted by one warp entirely in registers (rows or columns per lane, pivots and
 // multipliers exchanged with shuffles, no block barrier inside), the panel below is a per-row
@@ -548,128 +677,8 @@ k_rl_diag(const Region* __restrict__ regs, int kb, GpParams prm, double* __restr
         sX[r * LDS_ + c] = 0.0;
     }
     __syncthreads();
-    bool bad = false;
-#pragma unroll 1
-    for (int p = 0; p < 4; ++p) {
-        const int c0 = 16 * p;
-        // (a) 16x16 diagonal block: warp 0, lane r (and its mirror r+16) owns row r
-        if (warp == 0) {
-            const int r = lane & 15;
-            double a[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) a[k] = sL[(c0 + r) * LDS_ + c0 + k];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                double piv = __shfl_sync(0xffffffffu, a[c], c);
-                if (!(piv > 0.0)) {
-                    bad = true;
-                    piv = 1.0;
-                }
-                const double rs = rsqrt(piv);
-                const double l = a[c] * rs;                 // lane c: piv * rsqrt(piv) = sqrt(piv)
-#pragma unroll
-                for (int cc = c + 1; cc < 16; ++cc) a[cc] = fma(-l, __shfl_sync(0xffffffffu, l, cc), a[cc]);
-                a[c] = l;
-                if (lane == c) dinv[c0 + c] = rs;
-            }
-            if (lane < 16) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) sL[(c0 + r) * LDS_ + c0 + k] = (k <= r) ? a[k] : 0.0;
-            }
-        }
-        __syncthreads();
-        // (b) rows below the block: one thread per row, forward substitution against the 16x16 factor
-        const int nt = 48 - 16 * p;
-        if (tid < nt) {
-            const int r = c0 + 16 + tid;
-            double x[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = sL[r * LDS_ + c0 + k];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                double sum = x[c];
-#pragma unroll
-                for (int k = 0; k < c; ++k) sum = fma(-x[k], sL[(c0 + c) * LDS_ + c0 + k], sum);
-                x[c] = sum * dinv[c0 + c];
-            }
-#pragma unroll
-            for (int k = 0; k < 16; ++k) sL[r * LDS_ + c0 + k] = x[k];
-        }
-        __syncthreads();
-        // (c) trailing update of the lower triangle: thread = (row, strip of columns)
-        if (nt > 0) {
-            const int nstrip = GEMM_THREADS / nt;
-            const int rr = tid % nt, strip = tid / nt;
-            if (strip < nstrip) {
-                const int r = c0 + 16 + rr;
-                double lr[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) lr[k] = sL[r * LDS_ + c0 + k];
-                for (int cc = c0 + 16 + strip; cc <= r; cc += nstrip) {
-                    double sum = sL[r * LDS_ + cc];
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) sum = fma(-lr[k], sL[cc * LDS_ + c0 + k], sum);
-                    sL[r * LDS_ + cc] = sum;
-                }
-            }
-        }
-        __syncthreads();
-    }
+    const bool bad = chol_inv_64<LDS_>(sL, sX, dinv);
     if (bad && tid == 0) atomicOr(status + R.orig, GAPRO_GP_NOT_PSD);
-    // ---- inverse.  Diagonal 16x16 blocks: warp p, lane c (and mirror) owns column c.
-    {
-        const int c0 = 16 * warp, c = lane & 15;
-        double x[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            double sum = (q == c) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < q; ++k) sum = fma(-sL[(c0 + q) * LDS_ + c0 + k], x[k], sum);
-            x[q] = sum * dinv[c0 + q];
-        }
-        if (lane < 16) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) sX[(c0 + q) * LDS_ + c0 + c] = (q >= c) ? x[q] : 0.0;
-        }
-    }
-    __syncthreads();
-    // Off-diagonal blocks by distance d = i - j:  X_ij = -X_ii * sum_{k=j..i-1} L_ik X_kj.
-    // One warp per block; lane = (row r, half h of the 16 columns).
-#pragma unroll 1
-    for (int d = 1; d < 4; ++d) {
-        if (warp < 4 - d) {
-            const int i = warp + d, j = warp;
-            const int r = lane & 15, h = lane >> 4;
-            double t[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) t[q] = 0.0;
-            const double* Lrow = sL + (16 * i + r) * LDS_ + 16 * j;            // L[i-block row r][cols of blocks j..i-1]
-            for (int kk = 0; kk < 16 * d; ++kk) {
-                const double lv = Lrow[kk];
-                const double* xr = sX + (16 * j + kk) * LDS_ + 16 * j + 8 * h;  // X[(blocks j..i-1) row kk][block j cols]
-#pragma unroll
-                for (int q = 0; q < 8; ++q) t[q] = fma(lv, xr[q], t[q]);
-            }
-            // stage T in the destination block, then out = -X_ii * T
-            double* Tb = sX + (16 * i) * LDS_ + 16 * j;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) Tb[r * LDS_ + 8 * h + q] = t[q];
-            __syncwarp();
-            double o[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = 0.0;
-            const double* Xii = sX + (16 * i + r) * LDS_ + 16 * i;
-            for (int m = 0; m <= r; ++m) {
-                const double xv = Xii[m];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) o[q] = fma(-xv, Tb[m * LDS_ + 8 * h + q], o[q]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 8; ++q) Tb[r * LDS_ + 8 * h + q] = o[q];
-        }
-        __syncthreads();
-    }
     for (int e = tid; e < TB * TB; e += GEMM_THREADS) {
         const int rr = e >> 6, c = e & 63;
         const bool low = c <= rr;
@@ -1183,6 +1192,8 @@ k_adam_small(const Region* __restrict__ regs, GpParams prm, double* __restrict__
     }
 }
 
+#include "gp_small.cuh"
+
 // initial state: X, Z <- training rows (float32 widened), Xt <- test rows, y, m <- 1e-3 * noise, T <- I
 __global__ void __launch_bounds__(256)
 k_region_init(const Region* __restrict__ regs, int D, const float* __restrict__ feats, const int32_t* __restrict__ train_idx,
@@ -1344,6 +1355,8 @@ struct ChunkTables {
     std::vector<int> panel_prefix;  // panel tiles of the first cnt_gt[kb] regions
     int nbmax;
     int sweep_group;                // block steps whose trailing updates are applied in one pass
+    int n_small = 0;                // trailing single-tile regions trained by k_small_fit (they are the LAST regions of
+                                    // the size-sorted list and own exactly one entry of full / lower / rows / *_s)
 };
 
 
@@ -1543,14 +1556,15 @@ struct Driver {
 
     void build(const GpParams& p) {
         const int4* tiles = p.predict ? tb.wide : tb.full;
-        const int n = p.predict ? tb.n_wide : tb.n_full;
+        const int n = p.predict ? tb.n_wide : tb.n_full - tb.n_small;
+        if (n <= 0) return;
         k_build<<<n, 256, (TB * D + 2 * D * (TB + 1)) * sizeof(double), stream>>>(tb.regs, tiles, p, ws);
         ++g_launches;
     }
 
     void cholesky(const GpParams& p) {
         for (int kb = 0; kb < tb.nbmax; ++kb) {
-            const int live = tb.cnt_gt[kb];
+            const int live = tb.cnt_gt[kb] - ((kb == 0 && !p.predict) ? tb.n_small : 0);
             if (live <= 0) break;
             k_rl_diag<<<live, GEMM_THREADS, DIAG_SMEM, stream>>>(tb.regs, kb, p, ws, po.status);
             ++g_launches;
@@ -1569,14 +1583,16 @@ struct Driver {
     }
 
     void kgrad(const GpParams& p) {
+        const int nr = tb.n_rows - tb.n_small;
+        if (nr <= 0) return;
         if (D <= 6)
-            k_kgrad<6, 4><<<tb.n_rows * 2, 256, kgrad_smem<6, 4>(), stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad<6, 4><<<nr * 2, 256, kgrad_smem<6, 4>(), stream>>>(tb.regs, tb.rows, p, ws);
         else if (D <= 8)
-            k_kgrad<8, 4><<<tb.n_rows * 2, 256, kgrad_smem<8, 4>(), stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad<8, 4><<<nr * 2, 256, kgrad_smem<8, 4>(), stream>>>(tb.regs, tb.rows, p, ws);
         else if (D <= 32)
-            k_kgrad_wide<1><<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad_wide<1><<<nr, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         else
-            k_kgrad_wide<2><<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad_wide<2><<<nr, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
         ++g_launches;
     }
 
@@ -1600,19 +1616,21 @@ struct Driver {
             PHASE(cholesky(p))
         }
         to_lo();
-        PHASE((gemm<PH_A>(tb.full_s, tb.n_full_s, p), oz_phase<PH_A>(p)))
-        PHASE((gemm<PH_B>(tb.full_s, tb.n_full_s, p), oz_phase<PH_B>(p)))
-        PHASE((k_colstats<<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws, po), ++g_launches))
-        PHASE((gemm<PH_GA>(tb.full_s, tb.n_full_s, p), oz_phase<PH_GA>(p)))
-        PHASE((gemm<PH_GT>(tb.lower_s, tb.n_lower_s, p), oz_phase<PH_GT>(p)))
-        PHASE((k_grad_m<<<tb.n_rows, 256, 0, stream>>>(tb.regs, tb.rows, p, ws), ++g_launches))
-        PHASE((gemm<PH_GC>(tb.full_s, tb.n_full_s, p), oz_phase<PH_GC>(p)))
-        PHASE((gemm<PH_GL>(tb.lower_s, tb.n_lower_s, p), oz_phase<PH_GL>(p)))
+        const int nfs = tb.n_full_s - tb.n_small, nls = tb.n_lower_s - tb.n_small, nrw = tb.n_rows - tb.n_small;
+        const int nrg = n_regs - tb.n_small;
+        PHASE((gemm<PH_A>(tb.full_s, nfs, p), oz_phase<PH_A>(p)))
+        PHASE((gemm<PH_B>(tb.full_s, nfs, p), oz_phase<PH_B>(p)))
+        PHASE((nrw > 0 ? (k_colstats<<<nrw, 256, 0, stream>>>(tb.regs, tb.rows, p, ws, po), ++g_launches) : 0))
+        PHASE((gemm<PH_GA>(tb.full_s, nfs, p), oz_phase<PH_GA>(p)))
+        PHASE((gemm<PH_GT>(tb.lower_s, nls, p), oz_phase<PH_GT>(p)))
+        PHASE((nrw > 0 ? (k_grad_m<<<nrw, 256, 0, stream>>>(tb.regs, tb.rows, p, ws), ++g_launches) : 0))
+        PHASE((gemm<PH_GC>(tb.full_s, nfs, p), oz_phase<PH_GC>(p)))
+        PHASE((gemm<PH_GL>(tb.lower_s, nls, p), oz_phase<PH_GL>(p)))
         PHASE((void)0)   // (slot of the former L^T G_L product, folded into the previous phase)
-        PHASE((gemm<PH_Y>(tb.lower_s, tb.n_lower_s, p), oz_phase<PH_Y>(p)))   // G_K's lower tiles read only Y[k >= j]
-        PHASE((gemm<PH_GK>(tb.lower_s, tb.n_lower_s, p), oz_phase<PH_GK>(p)))
+        PHASE((gemm<PH_Y>(tb.lower_s, nls, p), oz_phase<PH_Y>(p)))   // G_K's lower tiles read only Y[k >= j]
+        PHASE((gemm<PH_GK>(tb.lower_s, nls, p), oz_phase<PH_GK>(p)))
         PHASE(kgrad(p))
-        PHASE((k_adam_small<<<n_regs, 256, 0, stream>>>(tb.regs, p, ws), ++g_launches))
+        PHASE((nrg > 0 ? (k_adam_small<<<nrg, 256, 0, stream>>>(tb.regs, p, ws), ++g_launches) : 0))
 #undef PHASE
         step_done();
     }
@@ -1896,6 +1914,7 @@ static int set_kernel_attributes() {
     if (done) return GAPRO_OK;
     int rc = allow_smem(k_build, (TB * 64 + 2 * 64 * (TB + 1)) * 8);
     if (rc == GAPRO_OK) rc = allow_smem(k_rl_diag, DIAG_SMEM);
+    if (rc == GAPRO_OK) rc = allow_smem(k_small_fit, SM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_rl_panel, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_rl_update, GEMM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_gemm<PH_A>, GEMM_SMEM);
@@ -1972,6 +1991,7 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             return GAPRO_ERR_WORKSPACE;
         }
         const int G = careful ? 1 : n_groups_for(chunk);
+        const bool small_path = !(getenv("GAPRO_GP_SMALL") && atoi(getenv("GAPRO_GP_SMALL")) == 0);
         if (G > 1 && (rc = ensure_pool()) != GAPRO_OK) return rc;
         // round-robin over the size-sorted list: every group sees the same size distribution
         std::vector<std::vector<Region>> groups(G);
@@ -2019,6 +2039,18 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             k_region_init<<<drv[g].n_regs, 256, 0, drv[g].stream>>>(drv[g].tb.regs, D, feats_spp, train_idx, test_idx,
                                                                     init_noise, drv[g].ws);
             ++g_launches;
+            // single-tile regions: all training steps in one launch, state in shared memory (gp_small.cuh).  They
+            // are the tail of the size-sorted list; the batched training kernels then skip them, prediction does not.
+            int n_small = 0;
+            if (small_path && D <= SM_DMAX && iters > 0 && stop_phase == 0 && !careful)
+                for (size_t i = groups[g].size(); i-- > 0 && groups[g][i].nb == 1;) ++n_small;
+            drv[g].tb.n_small = n_small;
+            if (n_small > 0) {
+                k_small_fit<<<n_small, SM_THREADS, SM_SMEM, drv[g].stream>>>(drv[g].tb.regs, drv[g].n_regs - n_small,
+                                                                            drv[g].params(1, 0), lr, iters, drv[g].ws,
+                                                                            po.status);
+                ++g_launches;
+            }
         }
         prof_end(stream);
         for (const Region& r : chunk) prof_account_train(r, iters);

@@ -702,3 +702,36 @@ def test_gp_fit_with_tcgen05_products_matches_golden(dev, lib, monkeypatch):
     assert rel_err(r[5].cpu().numpy(), g8["mu64"]) < TOL and rel_err(r[6].cpu().numpy(), g8["var64"]) < TOL
     sure = np.abs(g8["prob"] - 0.5) > EPS
     assert (r[2].cpu().numpy()[sure] == g8["label"][sure]).all()
+
+
+def test_small_region_kernel_against_numpy_mirror_and_batched_path(dev, lib, monkeypatch):
+    """north_star "one CTA per small region in shared memory": regions with M <= 64 are trained by k_small_fit (all
+    steps in one launch, six 64x64 float64 matrices resident in shared memory).  Three Adam steps against the numpy
+    mirror of the hand-derived gradient, and the whole fit against the batched tile path on the same regions."""
+    from gapro_b200.gaussian_process_utils import fit_gp_regions
+    from oracle import gp_oracle as G
+    for (cid, M, D, N) in [(31, 40, 6, 12), (32, 64, 6, 70), (33, 5, 3, 3)]:
+        X, n1, Xt, noise = gp_case(cid, M, D, N)
+        feats = torch.from_numpy(np.concatenate([X, Xt])).to(dev)
+        train, test = np.arange(M), np.arange(M, M + N)
+        Xd = X.astype(np.float64)
+        y = np.concatenate([-np.ones(n1), np.ones(M - n1)])
+        opt = G._Adam([Xd.copy(), 1e-3 * noise.astype(np.float64), np.eye(M), np.zeros(()), np.zeros(()), np.zeros(())], 0.1)
+        for _ in range(3):
+            p = opt.params
+            opt.step([np.asarray(g) for g in G.manual_grads(p[0], p[1], p[2], float(p[3]), float(p[4]), float(p[5]), Xd, y,
+                                                            1e-4, 1e-4)])
+        monkeypatch.setenv("GAPRO_GP_SMALL", "1")
+        s = _debug.gp_debug_state(feats, train, n1, test, noise, iters=3, stop_phase=0)
+        assert s["status"] == 0
+        assert rel_err(s["Z"], opt.params[0]) < 1e-8 and rel_err(s["m"], opt.params[1]) < 1e-7
+        assert rel_err(s["T"][:M, :M], opt.params[2]) < 1e-7
+        assert np.abs(s["scal"][:3] - np.array([float(p) for p in opt.params[3:]])).max() < 1e-9
+        assert np.abs(np.triu(s["T"], 1)).max() == 0 and (np.diag(s["T"])[M:] == 1).all()
+        small = fit_gp_regions(feats, [train], [n1], [test], init_noise=[noise], return_float64=True)[0]
+        monkeypatch.setenv("GAPRO_GP_SMALL", "0")
+        tiled = fit_gp_regions(feats, [train], [n1], [test], init_noise=[noise], return_float64=True)[0]
+        assert rel_err(small[5].cpu().numpy(), tiled[5].cpu().numpy()) < 1e-7
+        assert rel_err(small[6].cpu().numpy(), tiled[6].cpu().numpy()) < 1e-7
+        o = G.fit_region_autograd(X, n1, Xt, noise)
+        assert rel_err(small[5].cpu().numpy(), o["mu64"]) < TOL and rel_err(small[6].cpu().numpy(), o["var64"]) < TOL
