@@ -1045,98 +1045,135 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
     }
 }
 
-// Wide-feature variant (8 < D <= 64, e.g. the 32-d deep features of --use_deepfeat): lanes run over the
-// feature DIMENSION for the inducing-point gradient (no per-lane D-vector, no warp reduction over d)
-// and over the columns for the scalar sums.  The squared distance is recovered from the stored kernel
-// value, r^2 = -2 ln(K / s), so the D-wide difference is never formed.  One warp owns 8 rows.
+// Wide-feature variant (8 < D <= 64, e.g. the 32-d deep features of --use_deepfeat).  With D = 32 the
+// inducing-point gradient  dZ = -(W_zz Z + W_zx X),  W_zz = -G_K o K_zz,  W_zx = -1/2 G_C o K_zx,  is a real dense
+// contraction (K = M, N = D: 4 D / 32 = 4 flop per byte of the four M x M matrices it reads once) and runs on the
+// FP64 tensor pipe: a CTA owns 64 inducing rows, walks over the columns in chunks of 32, forms the two weight
+// blocks element-wise (thread = row quarter: 8 consecutive columns, so the global loads are 64-byte runs and the
+// per-row sums stay in registers), stages them and the Z / X rows of the chunk in shared memory and issues
+// mma.sync m8n8k4 (warp = 8 rows x all feature columns).  The next chunk's 4 x 8 values are loaded into registers
+// before the MMAs of the current one.  The squared distance for the lengthscale gradient is recovered from the stored
+// kernel value, r^2 = -2 ln(K / s).
+template <int NCH>
+constexpr int kgrad_wide_smem() { return (2 * 64 * 36 + 2 * 32 * (32 * NCH + 4) + 64) * (int)sizeof(double); }
+
 template <int NCH>
 __global__ void __launch_bounds__(256)
 k_kgrad_wide(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpParams prm, double* __restrict__ ws) {
-    constexpr int DP = 32 * NCH;
-    __shared__ double Zs[32][DP];
-    __shared__ double Xs[32][DP];
+    constexpr int DP = 32 * NCH, LDW = 36, LDF = DP + 4, NCB = DP / 8;
+    extern __shared__ __align__(16) double smem_kw[];
+    double* Wz = smem_kw;                               // weight blocks [64 rows][32 columns of the chunk]
+    double* Wx = Wz + 64 * LDW;
+    double* Zs = Wx + 64 * LDW;                         // rows jb .. jb+31 of Z and X, [32][D]
+    double* Xs = Zs + 32 * LDF;
+    double* s_cz = Xs + 32 * LDF;
     const int2 rt = rtiles[blockIdx.x];
     const Region R = regs[rt.x];
-    const int D = prm.D;
+    const int D = prm.D, M = R.M;
     const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
     double* base = ws + R.base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     const double* sc = base + lay.scal;
     const double ell = softplus_d(sc[SC_RL]), s = softplus_d(sc[SC_RS]);
     const double inv_l2 = 1.0 / (ell * ell), inv_s = 1.0 / s, m2_ell = -2.0 / ell;
     const double* Z = base + lay.Z;
     const double* X = base + lay.X;
-    const int row0 = rt.y * TB + warp * 8;
-    double az[8][NCH], as[8], al[8], cz[8];
+    const int row0 = rt.y * TB;
+    if (row0 >= M) return;
+    // element-wise role: row er, columns 8 * eq .. 8 * eq + 7 of the chunk
+    const int er = tid >> 2, eq = tid & 3;
+    const int i = row0 + er;
+    const double* g_gk = base + lay.Bm + (size_t)i * R.Wp + 8 * eq;
+    const double* g_kz = base + lay.Kc + (size_t)i * R.Mp + 8 * eq;
+    const double* g_gc = base + lay.GC + (size_t)i * R.Mp + 8 * eq;
+    const double* g_kx = base + lay.Kzx + (size_t)i * R.Wp + 8 * eq;
+    double2 pre[4][4];                                  // next chunk: 4 matrices x 8 doubles
+    auto fetch = [&](int jb) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        as[q] = al[q] = cz[q] = 0.0;
+        for (int u = 0; u < 4; ++u) {                   // rows and columns exist up to Mp (padded to 64): always in bounds
+            pre[0][u] = *reinterpret_cast<const double2*>(g_gk + jb + 2 * u);
+            pre[1][u] = *reinterpret_cast<const double2*>(g_kz + jb + 2 * u);
+            pre[2][u] = *reinterpret_cast<const double2*>(g_gc + jb + 2 * u);
+            pre[3][u] = *reinterpret_cast<const double2*>(g_kx + jb + 2 * u);
+        }
+    };
+    double acc[NCB][2];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) az[q][c] = 0.0;
-    }
-    for (int jb = 0; jb < R.M; jb += 32) {
-        __syncthreads();
-        for (int e = threadIdx.x; e < 32 * DP; e += blockDim.x) {
+    for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
+    double as = 0.0, al = 0.0, cz = 0.0;
+    const int nblk = (M + 31) >> 5;
+    fetch(0);
+    for (int b = 0; b < nblk; ++b) {
+        const int jb = 32 * b;
+        __syncthreads();                                // the previous chunk's MMAs have read the shared tiles
+        // Z / X rows of the chunk
+        for (int e = tid; e < 32 * DP; e += 256) {
             const int jj = e / DP, d = e - jj * DP;
-            const bool ok = (jb + jj < R.M) && d < D;
-            Zs[jj][d] = ok ? Z[(size_t)(jb + jj) * D + d] : 0.0;
-            Xs[jj][d] = ok ? X[(size_t)(jb + jj) * D + d] : 0.0;
+            const bool ok = (jb + jj < M) && d < D;
+            Zs[jj * LDF + d] = ok ? Z[(size_t)(jb + jj) * D + d] : 0.0;
+            Xs[jj * LDF + d] = ok ? X[(size_t)(jb + jj) * D + d] : 0.0;
         }
+        // weights of this thread's 8 elements
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = jb + 8 * eq + 2 * u + h;
+                const double gk = h ? pre[0][u].y : pre[0][u].x, kz = h ? pre[1][u].y : pre[1][u].x;
+                const double gc = h ? pre[2][u].y : pre[2][u].x, kx = h ? pre[3][u].y : pre[3][u].x;
+                double wz = 0.0, wx = 0.0;
+                if (i < M && j < M) {
+                    wz = -gk * kz;
+                    wx = -0.5 * gc * kx;
+                    as += (gk * kz + gc * kx) * inv_s;
+                    cz += wz + wx;
+                    const double r2z = kz > 0.0 ? -2.0 * log(kz * inv_s) : 0.0;     // r^2 (already divided by l^2)
+                    const double r2x = kx > 0.0 ? -2.0 * log(kx * inv_s) : 0.0;
+                    al += (0.5 * wz * r2z + wx * r2x) * m2_ell;
+                }
+                Wz[er * LDW + 8 * eq + 2 * u + h] = wz;
+                Wx[er * LDW + 8 * eq + 2 * u + h] = wx;
+            }
+        }
+        if (b + 1 < nblk) fetch(jb + 32);
         __syncthreads();
-        const int j = jb + lane;
-        double grz2[8], grx[8];
+        // acc(rows 8 warp + gid, feature columns) += Wz * Zs + Wx * Xs
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int i = row0 + q;
-            grz2[q] = grx[q] = 0.0;
-            if (i < R.M && j < R.M) {
-                const double gk = base[lay.Bm + (size_t)i * R.Wp + j], kz = base[lay.Kc + (size_t)i * R.Mp + j];
-                const double gc = base[lay.GC + (size_t)i * R.Mp + j], kx = base[lay.Kzx + (size_t)i * R.Wp + j];
-                grz2[q] = -gk * kz;
-                grx[q] = -0.5 * gc * kx;
-                as[q] += (gk * kz + gc * kx) * inv_s;
-                cz[q] += grz2[q] + grx[q];
-                const double r2z = kz > 0.0 ? -2.0 * log(kz * inv_s) : 0.0;     // r^2 (already divided by l^2)
-                const double r2x = kx > 0.0 ? -2.0 * log(kx * inv_s) : 0.0;
-                al[q] += (0.5 * grz2[q] * r2z + grx[q] * r2x) * m2_ell;
-            }
-        }
-#pragma unroll 4
-        for (int jj = 0; jj < 32; ++jj) {
-            double zv[NCH], xv[NCH];
+        for (int k0 = 0; k0 < 32; k0 += 4) {
+            const double az_ = Wz[(8 * warp + gid) * LDW + k0 + tig], ax_ = Wx[(8 * warp + gid) * LDW + k0 + tig];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                zv[c] = Zs[jj][lane + 32 * c];
-                xv[c] = Xs[jj][lane + 32 * c];
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const double gz = __shfl_sync(0xffffffffu, grz2[q], jj), gx = __shfl_sync(0xffffffffu, grx[q], jj);
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) az[q][c] = fma(-gz, zv[c], fma(-gx, xv[c], az[q][c]));
+            for (int c = 0; c < NCB; ++c) {
+                dmma(acc[c][0], acc[c][1], az_, Zs[(k0 + tig) * LDF + 8 * c + gid]);
+                dmma(acc[c][0], acc[c][1], ax_, Xs[(k0 + tig) * LDF + 8 * c + gid]);
             }
         }
     }
+    // per-row sums: the four threads of a row are consecutive lanes
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const int i = row0 + q;
-        double a0 = as[q], a1 = al[q], a2 = cz[q];
-        for (int o = 16; o; o >>= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    for (int o = 1; o < 4; o <<= 1) {
+        as += __shfl_xor_sync(0xffffffffu, as, o);
+        al += __shfl_xor_sync(0xffffffffu, al, o);
+        cz += __shfl_xor_sync(0xffffffffu, cz, o);
+    }
+    if (eq == 0) {
+        s_cz[er] = cz;
+        if (i < M) {
+            base[lay.gsrow + i] = as;
+            base[lay.glrow + i] = al;
         }
-        if (i < R.M) {
-            if (lane == 0) {
-                base[lay.gsrow + i] = a0;
-                base[lay.glrow + i] = a1;
-            }
+    }
+    __syncthreads();
+    // dZ[i][d] = 2 / l^2 * (cz_i z_i[d] - acc): this lane holds row 8 warp + gid, columns 8 c + 2 tig + {0, 1}
+    const int oi = row0 + 8 * warp + gid;
+    if (oi < M) {
+        const double czi = s_cz[8 * warp + gid];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const int d = lane + 32 * c;
-                if (d < D) base[lay.gZ + (size_t)i * D + d] = 2.0 * inv_l2 * fma(a2, Z[(size_t)i * D + d], az[q][c]);
+        for (int c = 0; c < NCB; ++c)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int d = 8 * c + 2 * tig + e;
+                if (d < D) base[lay.gZ + (size_t)oi * D + d] = 2.0 * inv_l2 * fma(czi, Z[(size_t)oi * D + d], -acc[c][e]);
             }
-        }
     }
 }
 
@@ -1428,6 +1465,7 @@ struct Driver {
     cudaStream_t s_hi = nullptr, s_lo = nullptr;
     cudaEvent_t ev_swept = nullptr, ev_stepped = nullptr;
     cudaEvent_t ev_prev_swept = nullptr;   // first sweep of the previous group: staggers the groups by one sweep
+    cudaEvent_t ev_small = nullptr;        // k_small_fit of this group has finished (it runs on its own stream)
     // careful mode (ONE region on the caller's stream, after the batched pass flagged it): every Cholesky is
     // checked on the host and retried with psd_safe_cholesky's jitter ladder
     bool careful = false;
@@ -1590,9 +1628,9 @@ struct Driver {
         else if (D <= 8)
             k_kgrad<8, 4><<<nr * 2, 256, kgrad_smem<8, 4>(), stream>>>(tb.regs, tb.rows, p, ws);
         else if (D <= 32)
-            k_kgrad_wide<1><<<nr, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad_wide<1><<<nr, 256, kgrad_wide_smem<1>(), stream>>>(tb.regs, tb.rows, p, ws);
         else
-            k_kgrad_wide<2><<<nr, 256, 0, stream>>>(tb.regs, tb.rows, p, ws);
+            k_kgrad_wide<2><<<nr, 256, kgrad_wide_smem<2>(), stream>>>(tb.regs, tb.rows, p, ws);
         ++g_launches;
     }
 
@@ -1639,6 +1677,7 @@ struct Driver {
         const GpParams p = params(0, 1);
         prof_begin(PROF_PREDICT, stream);
         to_hi();
+        if (ev_small) cudaStreamWaitEvent(stream, ev_small, 0);      // the small regions' trained state
         if (careful) {
             if (failed || factor_careful(p) != GAPRO_OK || failed) return;
         } else {
@@ -1851,6 +1890,8 @@ struct StreamPool {
     cudaEvent_t fork = nullptr, join[MAX_GROUPS] = {};
     cudaEvent_t swept[MAX_GROUPS] = {};
     cudaEvent_t stepped[MAX_GROUPS] = {};
+    cudaStream_t aux[MAX_GROUPS] = {};                       // the one-CTA-per-small-region kernel of a group
+    cudaEvent_t small_fork[MAX_GROUPS] = {}, small_done[MAX_GROUPS] = {};
     bool ready = false;
 };
 // streams and events belong to the device that was current when they were created: one pool per device
@@ -1873,6 +1914,9 @@ static int ensure_pool() {
         GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.join[i], cudaEventDisableTiming));
         GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.swept[i], cudaEventDisableTiming));
         GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.stepped[i], cudaEventDisableTiming));
+        GAPRO_CUDA_TRY(cudaStreamCreateWithPriority(&g_pool.aux[i], cudaStreamNonBlocking, least));
+        GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.small_fork[i], cudaEventDisableTiming));
+        GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.small_done[i], cudaEventDisableTiming));
     }
     GAPRO_CUDA_TRY(cudaEventCreateWithFlags(&g_pool.fork, cudaEventDisableTiming));
     g_pool.ready = true;
@@ -1946,13 +1990,13 @@ static int set_kernel_attributes() {
     if (rc == GAPRO_OK) rc = allow_smem(k_oz_slice_b<8>, 0);
     if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<6, 4>, kgrad_smem<6, 4>());
     if (rc == GAPRO_OK) rc = allow_smem(k_kgrad<8, 4>, kgrad_smem<8, 4>());
+    if (rc == GAPRO_OK) rc = allow_smem(k_kgrad_wide<1>, kgrad_wide_smem<1>());
+    if (rc == GAPRO_OK) rc = allow_smem(k_kgrad_wide<2>, kgrad_wide_smem<2>());
     if (!getenv("GAPRO_GP_DEFAULT_CARVEOUT")) {
         // the element-wise kernels too: a kernel that prefers a large L1 cannot share an SM with the tile
         // kernels of another group, which would serialise the side streams
         if (rc == GAPRO_OK) rc = allow_smem(k_colstats, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_grad_m, 0);
-        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad_wide<1>, 0);
-        if (rc == GAPRO_OK) rc = allow_smem(k_kgrad_wide<2>, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_adam_small, 0);
         if (rc == GAPRO_OK) rc = allow_smem(k_region_init, 0);
     }
@@ -2046,9 +2090,15 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
                 for (size_t i = groups[g].size(); i-- > 0 && groups[g][i].nb == 1;) ++n_small;
             drv[g].tb.n_small = n_small;
             if (n_small > 0) {
-                k_small_fit<<<n_small, SM_THREADS, SM_SMEM, drv[g].stream>>>(drv[g].tb.regs, drv[g].n_regs - n_small,
+                // on its own stream: ~50 dependent steps of one CTA each must not sit in front of the batched sweep
+                if ((rc = ensure_pool()) != GAPRO_OK) return rc;
+                GAPRO_CUDA_TRY(cudaEventRecord(g_pool.small_fork[g], drv[g].stream));
+                GAPRO_CUDA_TRY(cudaStreamWaitEvent(g_pool.aux[g], g_pool.small_fork[g], 0));
+                k_small_fit<<<n_small, SM_THREADS, SM_SMEM, g_pool.aux[g]>>>(drv[g].tb.regs, drv[g].n_regs - n_small,
                                                                             drv[g].params(1, 0), lr, iters, drv[g].ws,
                                                                             po.status);
+                GAPRO_CUDA_TRY(cudaEventRecord(g_pool.small_done[g], g_pool.aux[g]));
+                drv[g].ev_small = g_pool.small_done[g];
                 ++g_launches;
             }
         }
@@ -2064,6 +2114,8 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             for (int g = 0; g < G; ++g) drv[g].train_step(iters + 1, stop_phase);
         if (do_predict)
             for (int g = 0; g < G; ++g) drv[g].predict();
+        for (int g = 0; g < G; ++g)
+            if (drv[g].ev_small) GAPRO_CUDA_TRY(cudaStreamWaitEvent(stream, drv[g].ev_small, 0));
         if (G > 1)
             for (int g = 0; g < G; ++g) {
                 // whatever ran last on either stream of the group must be done
