@@ -286,8 +286,8 @@ def stage_rooflines(eng, lib, stream, flush):
     g_gbs = N * 28 / (g_ms * 1e-3) / 1e9
     out = {}
     for name, fn, nbytes in (
-        ("containment+occupancy (A+A')", occ, N * (24 + 4) + 48 * Bt + 4 * S * words + 4 * S),
-        ("containment+occupancy, round-1 by-superpoint gather kernel (not on the path)", occ_gather,
+        ("containment+occupancy (A+A')", occ_gather, N * (24 + 4) + 48 * Bt + 4 * S * words + 4 * S),
+        ("containment+occupancy, point-order alternative (GAPRO_OCCUPANCY=points, not the default path)", occ,
          N * (24 + 4) + 48 * Bt + 4 * S * words + 4 * S),
         ("feature pooling (B)", pool, N * (4 * D + 4) + 4 * S * D),
         ("broadcast (E)", bc, N * 4 + 16 * S + N * 12),
@@ -296,9 +296,9 @@ def stage_rooflines(eng, lib, stream, flush):
         gbs = nbytes / (ms * 1e-3) / 1e9
         out[name] = {"ms": ms, "algorithmic_bytes": int(nbytes), "achieved": gbs, "peak": peak, "unit": "GB/s",
                      "frac": gbs / peak, "peak_source": peak_src}
-    for name in ("feature pooling (B)",):
-        # reads N random 24-byte records + a coalesced index (index-ordered float32 sums need the points grouped by
-        # superpoint): the random-gather microbenchmark is shown next to the copy peak
+    for name in ("containment+occupancy (A+A')", "feature pooling (B)"):
+        # both read N random 24-byte records + a coalesced index (the points grouped by superpoint): the random-gather
+        # microbenchmark is shown next to the copy peak, which stays the roofline (`frac`)
         out[name]["random_gather_peak"] = g_gbs
         out[name]["frac_of_random_gather_peak"] = out[name]["achieved"] / g_gbs
     out["random 24-byte gather microbenchmark (gapro_gather_peak)"] = {

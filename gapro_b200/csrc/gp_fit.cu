@@ -508,6 +508,103 @@ k_build(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParam
     }
 }
 
+// Wide-feature variant (8 < D <= 64): the squared distances are a real dense contraction over the feature dimension,
+//   r^2(i, j) = |z_i|^2 + |x_j|^2 - 2 z_i . x_j   (clamped at 0, gpytorch's `sq_dist`),
+// and the dot products run on the FP64 tensor pipe: warp = 8 rows x 64 columns of the tile, mma.sync m8n8k4 over the
+// features, operands staged row-major in shared memory (row stride D + 4: conflict-free fragment loads).
+template <int NCH>
+constexpr int build_wide_smem() { return (3 * 64 * (32 * NCH + 4) + 3 * 64) * (int)sizeof(double); }
+
+template <int NCH>
+__global__ void __launch_bounds__(256)
+k_build_wide(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams prm, double* __restrict__ ws) {
+    constexpr int DP = 32 * NCH, LDZ = DP + 4;
+    extern __shared__ __align__(16) double smem_bw[];
+    double* zi = smem_bw;                // rows of the tile's row block     [64][LDZ]
+    double* zj = zi + 64 * LDZ;          // rows of Z of the column block
+    double* xj = zj + 64 * LDZ;          // rows of X (or the test rows) of the column block
+    double* ni = xj + 64 * LDZ;          // squared norms
+    double* nzj = ni + 64;
+    double* nxj = nzj + 64;
+    const int D = prm.D;
+    const int4 t = tiles[blockIdx.x];
+    const Region R = regs[t.x];
+    const int ti = t.y, tj = t.z;
+    const Layout lay = make_layout(R.Mp, R.Np, R.Wp, D);
+    double* base = ws + R.base;
+    const double* Z = base + lay.Z;
+    const double* Xc = prm.predict ? base + lay.Xt : base + lay.X;
+    const int ncols = prm.predict ? R.N : R.M;
+    const int colrows = prm.predict ? R.Np : R.Mp;
+    const bool do_zz = (tj <= ti) && (tj < R.nb);
+    const bool have_x = (tj + 1) * TB <= colrows;
+    for (int e = threadIdx.x; e < 64 * DP; e += 256) {
+        const int r = e / DP, d = e - r * DP;
+        const bool in = d < D;
+        zi[r * LDZ + d] = in ? Z[(size_t)(ti * TB + r) * D + d] : 0.0;
+        zj[r * LDZ + d] = (in && do_zz) ? Z[(size_t)(tj * TB + r) * D + d] : 0.0;
+        xj[r * LDZ + d] = (in && have_x) ? Xc[(size_t)(tj * TB + r) * D + d] : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x < 192) {
+        const double* v = (threadIdx.x < 64 ? zi : (threadIdx.x < 128 ? zj : xj)) + (threadIdx.x & 63) * LDZ;
+        double n = 0.0;
+        for (int d = 0; d < D; ++d) n = fma(v[d], v[d], n);
+        (threadIdx.x < 64 ? ni : (threadIdx.x < 128 ? nzj : nxj))[threadIdx.x & 63] = n;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    double az[8][2], ax[8][2];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) az[c][0] = az[c][1] = ax[c][0] = ax[c][1] = 0.0;
+#pragma unroll 2
+    for (int d0 = 0; d0 < DP; d0 += 4) {
+        const double a = zi[(8 * warp + gid) * LDZ + d0 + tig];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            dmma(ax[c][0], ax[c][1], a, xj[(8 * c + gid) * LDZ + d0 + tig]);
+            if (do_zz) dmma(az[c][0], az[c][1], a, zj[(8 * c + gid) * LDZ + d0 + tig]);
+        }
+    }
+    const double* sc = base + lay.scal;
+    const double ell = softplus_d(sc[SC_RL]), s = softplus_d(sc[SC_RS]);
+    const double inv_l2 = 1.0 / (ell * ell);
+    double* Kzx = base + lay.Kzx;
+    double* Kzz = base + lay.L;
+    double* Kc = base + lay.Kc;
+    const int lr = 8 * warp + gid, i = ti * TB + lr;
+    const double nrow = ni[lr];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int lc = 8 * c + 2 * tig, j = tj * TB + lc;
+        double kx[2], kz[2], k0[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double r2x = fmax(nrow + nxj[lc + e] - 2.0 * ax[c][e], 0.0);
+            kx[e] = (i < R.M && j + e < ncols) ? s * exp(-0.5 * (r2x * inv_l2)) : 0.0;
+            if (do_zz) {
+                if (i < R.M && j + e < R.M) {
+                    const double r2z = (i == j + e) ? 0.0 : fmax(nrow + nzj[lc + e] - 2.0 * az[c][e], 0.0);
+                    k0[e] = s * exp(-0.5 * (r2z * inv_l2));
+                    kz[e] = k0[e] + (i == j + e ? prm.jitter_zz : 0.0);
+                } else {
+                    k0[e] = 0.0;
+                    kz[e] = (i == j + e) ? 1.0 : 0.0;
+                }
+            }
+        }
+        *reinterpret_cast<double2*>(Kzx + (size_t)i * R.Wp + j) = make_double2(kx[0], kx[1]);
+        if (do_zz) {
+            *reinterpret_cast<double2*>(Kzz + (size_t)i * R.Mp + j) = make_double2(kz[0], kz[1]);
+            *reinterpret_cast<double2*>(Kc + (size_t)i * R.Mp + j) = make_double2(k0[0], k0[1]);
+            if (ti != tj) {
+                Kc[(size_t)j * R.Mp + i] = k0[0];
+                Kc[(size_t)(j + 1) * R.Mp + i] = k0[1];
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Blocked RIGHT-looking Cholesky with the inverse factor built alongside.  Block step kb is three
 // short launches whose tiles all contract over a single 64-wide block, so the critical path of a
@@ -1596,7 +1693,12 @@ struct Driver {
         const int4* tiles = p.predict ? tb.wide : tb.full;
         const int n = p.predict ? tb.n_wide : tb.n_full - tb.n_small;
         if (n <= 0) return;
-        k_build<<<n, 256, (TB * D + 2 * D * (TB + 1)) * sizeof(double), stream>>>(tb.regs, tiles, p, ws);
+        if (D > 32)
+            k_build_wide<2><<<n, 256, build_wide_smem<2>(), stream>>>(tb.regs, tiles, p, ws);
+        else if (D > 8)
+            k_build_wide<1><<<n, 256, build_wide_smem<1>(), stream>>>(tb.regs, tiles, p, ws);
+        else
+            k_build<<<n, 256, (TB * D + 2 * D * (TB + 1)) * sizeof(double), stream>>>(tb.regs, tiles, p, ws);
         ++g_launches;
     }
 
@@ -1957,6 +2059,8 @@ static int set_kernel_attributes() {
     bool& done = done_dev[dev];
     if (done) return GAPRO_OK;
     int rc = allow_smem(k_build, (TB * 64 + 2 * 64 * (TB + 1)) * 8);
+    if (rc == GAPRO_OK) rc = allow_smem(k_build_wide<1>, build_wide_smem<1>());
+    if (rc == GAPRO_OK) rc = allow_smem(k_build_wide<2>, build_wide_smem<2>());
     if (rc == GAPRO_OK) rc = allow_smem(k_rl_diag, DIAG_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_small_fit, SM_SMEM);
     if (rc == GAPRO_OK) rc = allow_smem(k_rl_panel, GEMM_SMEM);
