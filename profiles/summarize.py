@@ -69,6 +69,8 @@ COLS = OrderedDict([
     ("warps active %", "sm__warps_active.avg.pct_of_peak_sustained_active"),
     ("DMMA pipe %", "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active"),
     ("FP64 pipe %", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+    ("tensor pipe %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+    ("L2 throughput %", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("SM throughput %", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("DRAM read", "dram__bytes_read.sum"),
     ("DRAM write", "dram__bytes_write.sum"),

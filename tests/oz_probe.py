@@ -45,7 +45,7 @@ def main():
             opB = B.t() if tB else B
             ref = opA @ opB.t()
             bound = opA.abs().max(1)[0][:, None] * opB.abs().max(1)[0][None, :] * K
-            for S in (4, 5, 6, 7):
+            for S in (4, 5, 6, 7, 8):
                 C, ms_s, ms_g = oz_gemm(lib, A, tA, B, tB, S, reps=3 if M >= 1000 else 1)
                 err_b = float(((C - ref).abs() / bound).max())
                 err_n = float((C - ref).abs().max() / ref.abs().max())
