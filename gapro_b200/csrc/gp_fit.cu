@@ -1484,7 +1484,7 @@ struct ChunkTables {
     // the tile products of the training steps: small regions (DMMA tiles) / large regions (tcgen05, gp_ozaki.cuh)
     int4 *full_s, *lower_s, *oz_blk, *oz_full, *oz_lower;
     int2* oz_vb;
-    int n_full_s, n_lower_s, n_oz_vb, n_oz_blk, n_oz_full, n_oz_lower;
+    int n_full_s, n_lower_s, n_oz_vb, n_oz_blk, n_oz_full, n_oz_lower, oz_max_m = 0;
     std::vector<int> cnt_gt;        // cnt_gt[kb] = #regions with nb > kb
     std::vector<int> panel_prefix;  // panel tiles of the first cnt_gt[kb] regions
     int nbmax;
@@ -1628,12 +1628,14 @@ struct Driver {
     int ozS = 6;      // digits per operand of the tcgen05 path
 
     void oz_slice(int mat, int flags, int buf, const GpParams& p) {
-        k_oz_vecscale_b<<<tb.n_oz_vb, 256, 0, stream>>>(tb.regs, tb.oz_vb, p, ws, ozS, mat, flags, buf);
+        k_oz_zero_b<<<tb.n_oz_vb, 64, 0, stream>>>(tb.regs, tb.oz_vb, ws, ozS, buf);
+        k_oz_vecmax_b<<<dim3(tb.n_oz_vb, (tb.oz_max_m + OZ_KCH - 1) / OZ_KCH), 256, 0, stream>>>(tb.regs, tb.oz_vb, p, ws, ozS,
+                                                                                                mat, flags, buf);
         if (ozS == 5) k_oz_slice_b<5><<<tb.n_oz_blk, 256, 0, stream>>>(tb.regs, tb.oz_blk, p, ws, mat, flags, buf);
         else if (ozS == 6) k_oz_slice_b<6><<<tb.n_oz_blk, 256, 0, stream>>>(tb.regs, tb.oz_blk, p, ws, mat, flags, buf);
         else if (ozS == 7) k_oz_slice_b<7><<<tb.n_oz_blk, 256, 0, stream>>>(tb.regs, tb.oz_blk, p, ws, mat, flags, buf);
         else k_oz_slice_b<8><<<tb.n_oz_blk, 256, 0, stream>>>(tb.regs, tb.oz_blk, p, ws, mat, flags, buf);
-        g_launches += 2;
+        g_launches += 3;
     }
     template <int PH>
     void oz_gemm(bool lower, int abuf, int bbuf, const GpParams& p) {
@@ -1803,6 +1805,7 @@ int setup_chunk(std::vector<Region>& rs, char* aux, const char* aux_end, cudaStr
     std::vector<int4> full, lower, wide, full_s, lower_s, oz_blk, oz_full, oz_lower;
     std::vector<int2> rows, rowsp, panel, oz_vb;
     tb.nbmax = 0;
+    tb.oz_max_m = 0;
     for (size_t r = 0; r < rs.size(); ++r) tb.nbmax = std::max(tb.nbmax, rs[r].nb);
     tb.cnt_gt.assign(tb.nbmax + 1, 0);
     tb.panel_prefix.assign(tb.nbmax + 1, 0);
@@ -1821,6 +1824,7 @@ int setup_chunk(std::vector<Region>& rs, char* aux, const char* aux_end, cudaStr
         }
         if (R.oz) {
             const int kbt = (R.M + 63) / 64, t128 = (R.M + 127) / 128;
+            tb.oz_max_m = std::max(tb.oz_max_m, R.M);
             for (int vb = 0; vb < kbt; ++vb) oz_vb.push_back(make_int2((int)r, vb));
             for (int kb = 0; kb < kbt; ++kb)
                 for (int rb = 0; rb < kbt; ++rb) oz_blk.push_back(make_int4((int)r, kb, rb, 0));
@@ -2087,7 +2091,8 @@ static int set_kernel_attributes() {
     OZ_ATTR(7)
     OZ_ATTR(8)
 #undef OZ_ATTR
-    if (rc == GAPRO_OK) rc = allow_smem(k_oz_vecscale_b, 0);
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_vecmax_b, 0);
+    if (rc == GAPRO_OK) rc = allow_smem(k_oz_zero_b, 0);
     if (rc == GAPRO_OK) rc = allow_smem(k_oz_slice_b<5>, 0);
     if (rc == GAPRO_OK) rc = allow_smem(k_oz_slice_b<6>, 0);
     if (rc == GAPRO_OK) rc = allow_smem(k_oz_slice_b<7>, 0);

@@ -2,7 +2,7 @@
 // anonymous namespace; needs Region, Layout, GpParams, adam_update, Phase).
 //
 // A float64 product is evaluated from exact int8 digit-plane products (see ozaki.cu for the arithmetic and the
-// error bound).  Per training step of a large region: 14 operand slicings (k_oz_vecscale_b + k_oz_slice_b: every
+// error bound).  Per training step of a large region: 14 operand slicings (k_oz_vecmax_b + k_oz_slice_b: every
 // operand matrix in the orientation its product contracts over, scaled per row / column by a power of two) and
 // 8 launches of k_oz_gemm_b<PH> with the same fused epilogues as k_gemm<PH> (Adam on T, G_A assembly, the
 // symmetrisations).  The products contract over the same triangular k-ranges as the DMMA path, in 64-deep blocks.
@@ -46,41 +46,57 @@ __device__ __forceinline__ bool oz_valid(int v, int k, int M, int flags) {
     return true;
 }
 
-// scale[v] = 2^e, max_k |x(v, k)| 2^-e in [1/2, 1).  One CTA per (region, 64-vector block).
+// The scale buffer of an operand holds max_k |x(v, k)| per vector as a float64 bit pattern (positive doubles order like
+// unsigned integers): zeroed by k_oz_zero_b, raised by k_oz_vecmax_b with atomicMax - grid (64-vector block, k-chunk),
+// so that ONE large region still fills the GPU - and turned into the power-of-two scale 2^e, max 2^-e in [1/2, 1),
+// where it is used (oz_pow2).
+constexpr int OZ_KCH = 512;      // k-range of one k_oz_vecmax_b CTA
+
+__device__ __forceinline__ double oz_pow2(double m) { return (m > 0.0 && m < 1e300) ? ldexp(1.0, ilogb(m) + 1) : 1.0; }
+
+__global__ void __launch_bounds__(64)
+k_oz_zero_b(const Region* __restrict__ regs, const int2* __restrict__ vblocks, double* __restrict__ ws, int S, int buf) {
+    const int2 vb = vblocks[blockIdx.x];
+    const Region R = regs[vb.x];
+    oz_scale(ws, R, S, buf)[vb.y * 64 + threadIdx.x] = 0.0;
+}
+
 __global__ void __launch_bounds__(256)
-k_oz_vecscale_b(const Region* __restrict__ regs, const int2* __restrict__ vblocks, GpParams prm, double* __restrict__ ws,
-                int S, int mat, int flags, int buf) {
+k_oz_vecmax_b(const Region* __restrict__ regs, const int2* __restrict__ vblocks, GpParams prm, double* __restrict__ ws,
+              int S, int mat, int flags, int buf) {
     __shared__ double red[4][64];
     const int2 vb = vblocks[blockIdx.x];
     const Region R = regs[vb.x];
+    const int M = R.M;
+    const int k_lo = blockIdx.y * OZ_KCH, k_hi = min(M, k_lo + OZ_KCH);
+    if (k_lo >= M) return;
     const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
     const double* base = ws + R.base;
     int ld;
     const double* X = oz_src(lay, base, R, mat, ld);
     const double* ks = (flags & OZF_GV) ? base + lay.gv : nullptr;
-    double* scale = oz_scale(ws, R, S, buf);
-    const int M = R.M;
+    unsigned long long* mx = reinterpret_cast<unsigned long long*>(oz_scale(ws, R, S, buf));
     if (!(flags & OZF_TRANS)) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         for (int r = 0; r < 8; ++r) {
             const int v = vb.y * 64 + warp * 8 + r;
             if (v >= M) break;
             double m = 0.0;
-            for (int k = lane; k < M; k += 32) m = fmax(m, fabs(X[(size_t)v * ld + k] * (ks ? ks[k] : 1.0)));
+            for (int k = k_lo + lane; k < k_hi; k += 32) m = fmax(m, fabs(X[(size_t)v * ld + k] * (ks ? ks[k] : 1.0)));
             for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (lane == 0) scale[v] = m > 0.0 && m < 1e300 ? ldexp(1.0, ilogb(m) + 1) : 1.0;
+            if (lane == 0 && m > 0.0) atomicMax(mx + v, (unsigned long long)__double_as_longlong(m));
         }
     } else {
         const int c = threadIdx.x & 63, rg = threadIdx.x >> 6, v = vb.y * 64 + c;
         double m = 0.0;
         if (v < M)
-            for (int k = rg; k < M; k += 4)
+            for (int k = k_lo + rg; k < k_hi; k += 4)
                 if (oz_valid(v, k, M, flags)) m = fmax(m, fabs(X[(size_t)k * ld + v] * (ks ? ks[k] : 1.0)));
         red[rg][c] = m;
         __syncthreads();
         if (rg == 0 && v < M) {
             m = fmax(fmax(red[0][c], red[1][c]), fmax(red[2][c], red[3][c]));
-            scale[v] = m > 0.0 && m < 1e300 ? ldexp(1.0, ilogb(m) + 1) : 1.0;
+            if (m > 0.0) atomicMax(mx + v, (unsigned long long)__double_as_longlong(m));
         }
     }
 }
@@ -117,7 +133,7 @@ k_oz_slice_b(const Region* __restrict__ regs, const int4* __restrict__ blocks, G
     const int t = threadIdx.x;
     const int atom = t >> 5, r = (t & 31) >> 2, c = t & 3;
     const int v = 8 * atom + r;
-    const double inv = (v0 + v < M) ? 64.0 / scale[v0 + v] : 0.0;      // exact: a power of two
+    const double inv = (v0 + v < M) ? 64.0 / oz_pow2(scale[v0 + v]) : 0.0;      // exact: a power of two
     double y[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) y[j] = blk[v * LD + 16 * c + j + c] * inv;      // |y| < 64
@@ -226,7 +242,7 @@ k_oz_gemm_b(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpP
         const Layout lay = make_layout(R.Mp, R.Np, R.Wp, prm.D);
         double* base = ws + R.base;
         const int Mp = R.Mp, Wp = R.Wp, M = R.M;
-        const double sa = gr < M ? oz_scale(ws, R, S, abuf)[gr] : 0.0;
+        const double sa = gr < M ? oz_pow2(oz_scale(ws, R, S, abuf)[gr]) : 0.0;
         const double* sbv = oz_scale(ws, R, S, bbuf);
 #pragma unroll 1
         for (int c = 0; c < OZ_BN / 16; ++c) {
@@ -256,7 +272,7 @@ k_oz_gemm_b(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpP
             const int gc0 = tj * OZ_BN + 16 * c;
             if (gr >= Mp || gc0 >= Mp) continue;                // outside the allocated matrix (128-row tiles overhang)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = (gc0 + j < M) ? acc[j] * sa * sbv[gc0 + j] : 0.0;
+            for (int j = 0; j < 16; ++j) acc[j] = (gc0 + j < M) ? acc[j] * sa * oz_pow2(sbv[gc0 + j]) : 0.0;
             if (PH == PH_A || PH == PH_B) {
                 double* out = base + (PH == PH_A ? lay.A : lay.Bm) + (size_t)gr * Wp + gc0;
 #pragma unroll
