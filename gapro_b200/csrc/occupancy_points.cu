@@ -92,10 +92,10 @@ k_grid_build(const unsigned long long* __restrict__ extent_keys, const int32_t* 
     }
 }
 
-constexpr int OCC_T = 256, OCC_PER = 4;      // points per thread
+constexpr int OCC_T = 256, OCC_PER = 4;      // points per thread (their mask loads are issued together)
 
 template <int WORDS>
-__global__ void __launch_bounds__(OCC_T, 5)
+__global__ void __launch_bounds__(OCC_T, 4)
 k_occ_points(const double* __restrict__ xyz, const int32_t* __restrict__ spp_gid, const int64_t* __restrict__ pt_off,
              const int32_t* __restrict__ box_off, const double* __restrict__ boxes, const SceneGrid* __restrict__ grids,
              const uint32_t* __restrict__ full_mask, const uint32_t* __restrict__ cand_mask, int n_scenes, int64_t n,
@@ -123,15 +123,20 @@ k_occ_points(const double* __restrict__ xyz, const int32_t* __restrict__ spp_gid
     }
     __syncthreads();
     // scene of the chunk's first point; later points only move forward
-    int sc = gapro_find_segment<int64_t>(pt_off, n_scenes, base);
+    const int sc = gapro_find_segment<int64_t>(pt_off, n_scenes, base);
     constexpr int stride = 32 * WORDS;
+    // phase 1: cell of every point of this thread and its two masks - all loads in flight together
+    int scn[OCC_PER];
+    uint32_t fm[OCC_PER][WORDS], cm[OCC_PER][WORDS];
 #pragma unroll
     for (int q = 0; q < OCC_PER; ++q) {
         const int k = q * OCC_T + threadIdx.x;
-        if (k >= npts) break;
+        scn[q] = -1;
+        if (k >= npts) continue;
         const int64_t p = base + k;
         int s = sc;
         while (p >= pt_off[s + 1]) ++s;
+        scn[q] = s;
         const double x = s_xyz[3 * k], y = s_xyz[3 * k + 1], z = s_xyz[3 * k + 2];
         const SceneGrid G = grids[s];
         int ix = (int)((x - G.x0) * G.inv_dx), iy = (int)((y - G.y0) * G.inv_dy), iz = (int)((z - G.z0) * G.inv_dz);
@@ -139,12 +144,24 @@ k_occ_points(const double* __restrict__ xyz, const int32_t* __restrict__ spp_gid
         iy = iy < 0 ? 0 : (iy > GY - 1 ? GY - 1 : iy);
         iz = iz < 0 ? 0 : (iz > GZ - 1 ? GZ - 1 : iz);
         const size_t cell = ((size_t)s * CELLS + (size_t)(iz * GY + iy) * GX + ix) * WORDS;
-        const int b0 = box_off[s];
+#pragma unroll
+        for (int w = 0; w < WORDS; ++w) {
+            fm[q][w] = __ldg(full_mask + cell + w);
+            cm[q][w] = __ldg(cand_mask + cell + w);
+        }
+    }
+    // phase 2: exact float64 test for the boxes whose boundary crosses the cell, then the integer reductions
+#pragma unroll
+    for (int q = 0; q < OCC_PER; ++q) {
+        if (scn[q] < 0) continue;
+        const int k = q * OCC_T + threadIdx.x;
+        const double x = s_xyz[3 * k], y = s_xyz[3 * k + 1], z = s_xyz[3 * k + 2];
+        const int b0 = box_off[scn[q]];
         int32_t* row = cnt_table + (size_t)gid[q] * stride;
 #pragma unroll
         for (int w = 0; w < WORDS; ++w) {
-            uint32_t m = __ldg(full_mask + cell + w);
-            uint32_t c = __ldg(cand_mask + cell + w);
+            uint32_t m = fm[q][w];
+            uint32_t c = cm[q][w];
             while (c) {
                 const int bb = __ffs(c) - 1;
                 c &= c - 1;

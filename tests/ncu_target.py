@@ -19,7 +19,9 @@ def _cfg(i):
     return synthetic.c3_config(i) if cfg == "c3" else cfg
 
 
-scenes = [to_scene_inputs(synthetic_inputs(synthetic.make_scene(1000 + i, _cfg(i))), dev, noise_seed=i) for i in range(n)]
+deep = cfg == "c1_deep"
+scenes = [to_scene_inputs(synthetic_inputs(synthetic.make_scene(1000 + i, _cfg(i)), use_deepfeat=deep), dev, noise_seed=i)
+          for i in range(n)]
 eng.run(scenes, thresh_spp_occu=0.999, training_iter=iters)
 torch.cuda.synchronize()
 print("done", eng.last_stats["n_regions"], eng.last_stats["launches"])
