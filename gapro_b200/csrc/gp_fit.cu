@@ -1366,10 +1366,11 @@ static int oz_digits() {
     return s < 5 ? 5 : (s > 8 ? 8 : s);
 }
 static int oz_min_rows() {
-    // Opt-in (GAPRO_GP_OZAKI=1): the digit-plane products are normwise-accurate, but the 50-step Adam trajectory
-    // amplifies their error (relative to row-max x column-max x K instead of float64's componentwise bound) beyond
-    // the 1e-6 parity bar of the test-suite for the largest regions - see DESIGN.md section 4 for the measurements.
-    int on = 0, m = 2048;
+    // Regions with at least this many padded training rows run their tile products on tcgen05 (8 digits: the same
+    // 1e-6 parity bar as the DMMA path on the 8k-superpoint golden region, 1.27x faster on the configs[3] / configs[4]
+    // workloads; below ~2000 rows the slicing passes eat the gain - DESIGN.md section 4.1).  GAPRO_GP_OZAKI=0 turns
+    // the path off, GAPRO_GP_OZAKI_MIN_M moves the threshold.
+    int on = 1, m = 2048;
     if (const char* e = getenv("GAPRO_GP_OZAKI")) on = atoi(e);
     if (const char* e = getenv("GAPRO_GP_OZAKI_MIN_M")) m = atoi(e);
     return on ? m : (1 << 30);

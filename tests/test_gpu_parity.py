@@ -497,9 +497,12 @@ def test_extension_is_the_code_that_ran(engine):
 
 
 # ------------------------------------------------------------------- BASELINE.json sizes (round 2)
-def test_gp_region_of_8k_superpoints_matches_golden(dev, lib):
+@pytest.mark.parametrize("tcgen05", ["1", "0"])
+def test_gp_region_of_8k_superpoints_matches_golden(dev, lib, tcgen05, monkeypatch):
     """configs[3]: M = 4200 training rows + 3800 test rows (66 blocks of 64, ~2 GB of region state) against the
-    committed fp64-oracle vectors (tests/golden/make_golden_fullsize.py)."""
+    committed fp64-oracle vectors (tests/golden/make_golden_fullsize.py) - on the default path for this size (tile
+    products on tcgen05 digit planes) and on the FP64 DMMA path (GAPRO_GP_OZAKI=0)."""
+    monkeypatch.setenv("GAPRO_GP_OZAKI", tcgen05)
     from gapro_b200.gaussian_process_utils import fit_gp_regions
     from tests.golden.make_golden_fullsize import GP_8K
     gold = np.load(os.path.join(GOLD_DIR, "gp_case_8k.npz"))
@@ -679,9 +682,9 @@ def test_tcgen05_digit_plane_product_matches_float64(dev, lib):
 
 
 def test_gp_fit_with_tcgen05_products_matches_golden(dev, lib, monkeypatch):
-    """GAPRO_GP_OZAKI=1: the seven tile products of every training step of large regions run on tcgen05 (8 digits).
-    Same golden fp64-oracle vectors and the same 1e-6 bar as the default DMMA path: M = 1000 and the 8k-superpoint
-    region (M = 4200)."""
+    """The tile products of every training step of large regions run on tcgen05 (8 digits; default from 2048 padded
+    rows, here forced from 512).  Same golden fp64-oracle vectors and the same 1e-6 bar as the DMMA path: M = 1000 and
+    the 8k-superpoint region (M = 4200)."""
     from gapro_b200.gaussian_process_utils import fit_gp_regions
     from tests.golden.make_golden import GP_CASES_LARGE
     from tests.golden.make_golden_fullsize import GP_8K
