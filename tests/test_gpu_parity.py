@@ -514,7 +514,9 @@ def test_gp_region_of_8k_superpoints_matches_golden(dev, lib, tcgen05, monkeypat
     assert rel_err(r[6].cpu().numpy(), gold["var64"]) < TOL
     sure = np.abs(gold["prob"] - 0.5) > EPS
     assert (r[2].cpu().numpy()[sure] == gold["label"][sure]).all()
-    assert np.allclose(r[0].cpu().numpy(), gold["prob"], rtol=1e-6, atol=1e-7)
+    # float32 class probability: 1e-7 (two float32 ulps) on the DMMA path; the digit-plane path is at 4e-7 relative in
+    # mu / var here, i.e. a few float32 ulps in p
+    assert np.allclose(r[0].cpu().numpy(), gold["prob"], rtol=1e-6, atol=1e-7 if tcgen05 == "0" else 1e-6)
 
 
 @pytest.mark.parametrize("tag", ["c1", "c3"])
