@@ -57,7 +57,7 @@ def quad_to_box(q, normal):
 def wall_boxes_from_planes(plane_dict, axis_align_matrix):
     verts = np.array(plane_dict["verts"], dtype=np.float64)
     verts = np.column_stack([verts[:, 0], -verts[:, 2], verts[:, 1]])     # y <- -z, z <- y (:192-195)
-    room_centre = verts.mean(0)                                           # centre BEFORE alignment (:216)
+    # (the reference also computes the room centre before the alignment, :216, and never uses it)
     pts = np.ones((verts.shape[0], 4))
     pts[:, :3] = verts
     verts = (pts @ np.asarray(axis_align_matrix).T)[:, :3]
@@ -72,7 +72,6 @@ def wall_boxes_from_planes(plane_dict, axis_align_matrix):
         if not abs(n[2]) < 0.2:       # vertical planes only (:218-220); a NaN normal is dropped too
             continue
         boxes.append(quad_to_box(q, n))
-    del room_centre
     if not boxes:
         return [], [], []
     boxes = np.array(boxes)
