@@ -557,7 +557,7 @@ def run_gpu(args):
         # fresh interpreter with the GPUs hidden: this process holds a CUDA context and must not fork workers
         env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
                                 "--warmup", "0", "--workload", args.workload, "--scenes", str(args.scenes),
                                 "--mode", args.mode, "--total-scenes", str(args.total_scenes)],
                                env=env, capture_output=True, text=True, timeout=300)
@@ -602,7 +602,7 @@ def main():
                          "(32: the heaviest scene alone exceeds an eighth of the job)")
     ap.add_argument("--scenes", type=int, default=8, help="scenes per GPU pass (and per GPU per step in weak mode)")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=5, help="steps of the end-to-end timing (at most --steps)")
+    ap.add_argument("--e2e-steps", type=int, default=3, help="steps of the end-to-end timing (at most --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()

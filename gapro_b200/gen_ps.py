@@ -41,14 +41,24 @@ def read_axis_align_matrix(meta_file: str) -> np.ndarray:
 
 
 def prepare_inputs(xyz, rgb, semantic_label, instance_label, spp, axis_align_matrix, wall_box=None,
-                   wall_volume=None, deep_feats=None, dataset_name="scannetv2"):
+                   wall_volume=None, deep_feats=None, dataset_name="scannetv2", device_boxes=False):
     """Host steps of gen_ps.py:48-77 on numpy arrays.  NOTE the reference builds the GP features
-    from the UN-aligned xyz (concat at :55 happens before the alignment at :66-69); kept."""
+    from the UN-aligned xyz (concat at :55 happens before the alignment at :66-69); kept.
+    device_boxes=True leaves getInstanceInfo (:72-74) to the GPU: the labels travel with the scene and
+    `to_scene_inputs` derives the boxes there (gapro_instance_info)."""
     xyz = np.asarray(xyz)
     mask_feats = np.asarray(deep_feats) if deep_feats is not None else np.concatenate([xyz, np.asarray(rgb)], axis=-1)
     pts = np.ones((xyz.shape[0], 4))
     pts[:, 0:3] = xyz[:, 0:3]
     xyz_al = np.dot(pts, np.asarray(axis_align_matrix).transpose())[:, :3]
+    if device_boxes:
+        inst = np.asarray(instance_label, dtype=np.float64)
+        if not np.any(inst >= 0):
+            raise ValueError("scene has no labelled instance (getInstanceInfo returned None, gen_ps_utils.py:229-230)")
+        return dict(xyz=xyz_al, mask_feats=mask_feats, spp=np.asarray(spp), instance_label=inst,
+                    semantic_label=np.asarray(semantic_label, dtype=np.float64), dataset_name=dataset_name,
+                    wall_box=wall_box if wall_box is not None else [],
+                    wall_volume=wall_volume if wall_volume is not None else [])
     info = getInstanceInfo(xyz_al, instance_label=instance_label, semantic_label=semantic_label,
                            dataset_name=dataset_name)
     if info is None:
@@ -70,13 +80,24 @@ def to_scene_inputs(inp: dict, device, noise_seed=None, pin=False) -> SceneInput
 
     wall_box, wall_vol = inp["wall_box"], inp["wall_volume"]
     has_wall = len(wall_box) > 0
+    coords = dev(inp["xyz"], torch.float64)
+    if "instance_box" in inp:
+        cls, box, vol = (dev(inp["instance_cls"], torch.int64), dev(inp["instance_box"], torch.float32),
+                         dev(inp["instance_box_volume"], torch.float32))
+    else:       # boxes from the labelled points on the device (getInstanceInfo, gen_ps.py:72-74), then the casts of :79-81
+        from .gen_ps_utils import getInstanceInfo_cuda
+        info = getInstanceInfo_cuda(coords, dev(inp["instance_label"], torch.float64), dev(inp["semantic_label"], torch.float64),
+                                    dataset_name=inp.get("dataset_name", "scannetv2"))
+        if info is None:
+            raise ValueError("scene has no labelled instance (getInstanceInfo returned None, gen_ps_utils.py:229-230)")
+        cls, box, vol = info[1].long(), info[2].float(), info[3].float()
     return SceneInputs(
-        coords_float=dev(inp["xyz"], torch.float64),
+        coords_float=coords,
         mask_feats=dev(inp["mask_feats"], torch.float32),
         spp=dev(inp["spp"], torch.int64),
-        instance_cls=dev(inp["instance_cls"], torch.int64),
-        instance_box=dev(inp["instance_box"], torch.float32),
-        instance_box_volume=dev(inp["instance_box_volume"], torch.float32),
+        instance_cls=cls,
+        instance_box=box,
+        instance_box_volume=vol,
         wall_box=dev(wall_box, torch.float32) if has_wall else [],
         wall_box_volume=dev(wall_vol, torch.float32) if has_wall else [],
         noise_seed=noise_seed,
@@ -90,7 +111,7 @@ def synthetic_inputs(scene, use_deepfeat=False) -> dict:
                           deep_feats=scene.deep_feats if use_deepfeat else None)
 
 
-def load_scene(filename, scan_name, use_deepfeat=False, deepfeat_folder=None, data_root=DATA_ROOT):
+def load_scene(filename, scan_name, use_deepfeat=False, deepfeat_folder=None, data_root=DATA_ROOT, device_boxes=False):
     """Disk -> host arrays for one scene (gen_ps.py:45-77): scene tuple, superpoints, optional deep
     features, axis alignment, instance boxes, optional wall boxes.  Returns (inputs, sem, inst)."""
     from .scannet_planes import get_wall_boxes
@@ -100,7 +121,7 @@ def load_scene(filename, scan_name, use_deepfeat=False, deepfeat_folder=None, da
     A = read_axis_align_matrix(osp.join(data_root, "scans_transform", scan_name, scan_name + ".txt"))
     _, wall_box, wall_vol = get_wall_boxes(scan_name, planes_root=osp.join(data_root, "scannet_planes"),
                                            transform_root=osp.join(data_root, "scans_transform"))
-    return prepare_inputs(xyz, rgb, sem, inst, spp, A, wall_box, wall_vol, deep), sem, inst
+    return prepare_inputs(xyz, rgb, sem, inst, spp, A, wall_box, wall_vol, deep, device_boxes=device_boxes), sem, inst
 
 
 def save_pseudo_labels(path, result, per_point_uncertainty=False, spp_dense=None):
@@ -126,7 +147,8 @@ def _dist_env():
 def _load_batch(pool, chunk, args):
     """Disk -> host for a batch on worker threads; a scene that cannot be loaded (missing file, no labelled
     instance - SURVEY Q9, where the reference crashes) is reported and skipped, the rest of the batch goes on."""
-    futs = [pool.submit(load_scene, fn, scan, args.use_deepfeat, args.deepfeat_folder) for fn, scan in chunk]
+    futs = [pool.submit(load_scene, fn, scan, args.use_deepfeat, args.deepfeat_folder, DATA_ROOT, args.device_boxes)
+            for fn, scan in chunk]
 
     def collect():
         out = []
@@ -181,6 +203,9 @@ def main(argv=None):
                         help="K_ZZ jitter of the variational strategy: 1e-4 is gpytorch >= 1.6 (float32 "
                              "settings.variational_cholesky_jitter), 1e-3 the add_jitter() default of gpytorch <= 1.5; "
                              "the reference does not pin a gpytorch version")
+    parser.add_argument("--device_boxes", action="store_true",
+                        help="derive the instance boxes from the labelled points on the GPU (gapro_instance_info) "
+                             "instead of in the host loader threads; identical boxes")
     parser.add_argument("--balance", choices=["cost", "static"], default="cost",
                         help="multi-GPU sharding: LPT by a cost estimated from the cheap stages, or round-robin")
     args = parser.parse_args(argv)

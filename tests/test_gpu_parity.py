@@ -486,6 +486,13 @@ def test_cli_end_to_end_on_a_reference_shaped_dataset(dev, lib, tmp_path, monkey
         assert np.allclose(prob, ref[2], rtol=1e-5) and mu.shape == ref[3].shape
         g = ref[3] != -100
         assert np.allclose(mu[g], ref[3][g], rtol=1e-4, atol=0) and np.allclose(var[g], ref[4][g], rtol=1e-4, atol=0)
+    # the same job with the boxes derived from the labelled points on the GPU: identical files
+    save2 = tmp_path / "out_device_boxes"
+    gen_ps.main(["--save_folder", str(save2), "--seed", "7", "--batch_scenes", "2", "--device_boxes"])
+    for scan in ("scene0000_00", "scene0002_01"):
+        a = torch.load(str(save / f"{scan}.pth"), weights_only=False)
+        b = torch.load(str(save2 / f"{scan}.pth"), weights_only=False)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
 def test_extension_is_the_code_that_ran(engine):
