@@ -377,18 +377,28 @@ k_gemm(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpParams
         double* Tv = base + lay.Tv;
         const double invN = 1.0 / (double)R.M;
         ACC_FOREACH(true, true, r0, c0, {
-            _Pragma("unroll") for (int e = 0; e < 2; ++e) {
-                const int cc = col + e;
-                if (row < R.M && cc <= row) {
-                    const size_t idx = (size_t)row * Mp + cc;
-                    double p = T[idx];
-                    double g = 2.0 * (e ? v1 : v0) + (p - (cc == row ? 1.0 / p : 0.0)) * invN;
-                    double m1 = Tm[idx], m2 = Tv[idx];
-                    adam_update(p, m1, m2, g, prm);
-                    T[idx] = p;
-                    Tm[idx] = m1;
-                    Tv[idx] = m2;
-                }
+            if (row < R.M && col + 1 <= row) {
+                // both elements of the pair lie in the lower triangle (col is even; the second one may be the diagonal):
+                // 128-bit loads / stores of T and its two Adam moments
+                const size_t idx = (size_t)row * Mp + col;
+                double2 p = *reinterpret_cast<const double2*>(T + idx);
+                double2 m1 = *reinterpret_cast<const double2*>(Tm + idx), m2 = *reinterpret_cast<const double2*>(Tv + idx);
+                const double ga = 2.0 * v0 + p.x * invN;
+                const double gb = 2.0 * v1 + (p.y - (col + 1 == row ? 1.0 / p.y : 0.0)) * invN;
+                adam_update(p.x, m1.x, m2.x, ga, prm);
+                adam_update(p.y, m1.y, m2.y, gb, prm);
+                *reinterpret_cast<double2*>(T + idx) = p;
+                *reinterpret_cast<double2*>(Tm + idx) = m1;
+                *reinterpret_cast<double2*>(Tv + idx) = m2;
+            } else if (row < R.M && col <= row) {      // col == row: the diagonal element alone
+                const size_t idx = (size_t)row * Mp + col;
+                double p = T[idx];
+                const double g = 2.0 * v0 + (p - 1.0 / p) * invN;
+                double m1 = Tm[idx], m2 = Tv[idx];
+                adam_update(p, m1, m2, g, prm);
+                T[idx] = p;
+                Tm[idx] = m1;
+                Tv[idx] = m2;
             }
         })
     } else if (PH == PH_GC) {  // G_C = Linv^T * G_A: k >= i
