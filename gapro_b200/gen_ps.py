@@ -194,7 +194,7 @@ def main(argv=None):
     parser.add_argument("--deepfeat_folder", type=str, default=osp.join(DATA_ROOT, "pretrain_maskfeats2"))
     parser.add_argument("--eval_pslabel", action="store_true")
     # additions
-    parser.add_argument("--batch_scenes", type=int, default=8, help="scenes per GPU pass")
+    parser.add_argument("--batch_scenes", type=int, default=16, help="scenes per GPU pass")
     parser.add_argument("--seed", type=int, default=None, help="seed of the GP initialisation noise")
     parser.add_argument("--load_workers", type=int, default=8, help="host threads reading / preparing the next batch")
     parser.add_argument("--per_point_uncertainty", action="store_true",
