@@ -148,7 +148,7 @@ def run_reference(args):
     import multiprocessing as mp
     n_workers = len(os.sched_getaffinity(0))
     ids = scene_ids(args, world)
-    budget = max(4.0, min(30.0, 150.0 / max(args.steps + args.warmup, 1)))
+    budget = args.cpu_budget or max(4.0, min(30.0, 150.0 / max(args.steps + args.warmup, 1)))
     ctx = mp.get_context("fork")
     rng = np.random.default_rng(0)
     spent, fracs, log = [], [], []
@@ -372,7 +372,7 @@ def run_gpu(args):
             part = mine[i0:i0 + args.scenes]
             st = eng.run([to_scene_inputs(make_input(i, args.workload), dev) for i in part], plan_only=True, **kw)
             for k, i in enumerate(part):
-                est[i] = sharding.scene_cost(st["sum_m3"][k], st["n_points"][k], st["n_regions"][k])
+                est[i] = sharding.scene_cost(st["sum_m3"][k], st["n_points"][k], st["n_regions"][k], st["sum_m2"][k])
         merged = {}
         for d in sharding.gather_records([est], world):
             merged.update(d)
@@ -557,7 +557,9 @@ def run_gpu(args):
         # fresh interpreter with the GPUs hidden: this process holds a CUDA context and must not fork workers
         env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+            # two scenes of the list (a heavy and a typical one), ~15 s of CPU work each
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
+                                "--cpu-budget", "15",
                                 "--warmup", "0", "--workload", args.workload, "--scenes", str(args.scenes),
                                 "--mode", args.mode, "--total-scenes", str(args.total_scenes)],
                                env=env, capture_output=True, text=True, timeout=300)
@@ -605,6 +607,7 @@ def main():
                          "6.73 / 6.71 scenes/s with passes of 8 / 16 / 24 / 48 scenes")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=3, help="steps of the end-to-end timing (at most --steps)")
+    ap.add_argument("--cpu-budget", type=float, default=None, help="seconds of CPU work per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()

@@ -253,6 +253,7 @@ class GaproEngine:
             m = (m1 + m2).astype(np.float64)
             rs = pl["region_scene"]
             return dict(sum_m3=np.bincount(rs, weights=m ** 3, minlength=ns)[:ns] if R else np.zeros(ns),
+                        sum_m2=np.bincount(rs, weights=m ** 2, minlength=ns)[:ns] if R else np.zeros(ns),
                         n_regions=np.bincount(rs, minlength=ns)[:ns] if R else np.zeros(ns, np.int64),
                         max_m=np.array([m[rs == i].max() if np.any(rs == i) else 0 for i in range(ns)]),
                         n_points=np.array(n_pts), n_spp=np.diff(spp_off).astype(np.int64))

@@ -183,7 +183,7 @@ def estimate_costs(items, args, device, pool):
         scenes = [to_scene_inputs(inp[0], device, pin=True) for _, inp in ok]
         st = eng.run(scenes, thresh_spp_occu=0.999, plan_only=True)
         for k, (scan, _) in enumerate(ok):
-            costs[scan] = scene_cost(st["sum_m3"][k], st["n_points"][k], st["n_regions"][k])
+            costs[scan] = scene_cost(st["sum_m3"][k], st["n_points"][k], st["n_regions"][k], st["sum_m2"][k])
     return costs
 
 

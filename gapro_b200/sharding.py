@@ -6,15 +6,19 @@ from __future__ import annotations
 
 from typing import List, Sequence
 
-# seconds of one B200 per unit of sum(M^3) and per point, for turning the stage-pass statistics into a cost:
-# the GP stage is ~385 * M^3 flops per region at ~25 TFLOP/s; everything else is per point / per launch.
-COST_PER_M3 = 385.0 / 25e12
+# seconds of one B200 per unit of sum(M^3), sum(M^2), per point and per region, for turning the stage-pass statistics
+# into a cost.  From the event-timed phases of the bench pass (sum M^3 = 9.85e10, sum M^2 = 9.5e7, 50 steps): tile
+# products + Cholesky sweep 1445 ms ~ M^3, kernel build / gradient / column statistics 100 ms ~ M^2; the rest is per
+# point / per launch.
+COST_PER_M3 = 1.47e-11
+COST_PER_M2 = 1.05e-9
 COST_PER_POINT = 2e-8
 COST_PER_REGION = 2e-5
 
 
-def scene_cost(sum_m3: float, n_points: float = 0.0, n_regions: float = 0.0) -> float:
-    return COST_PER_M3 * float(sum_m3) + COST_PER_POINT * float(n_points) + COST_PER_REGION * float(n_regions)
+def scene_cost(sum_m3: float, n_points: float = 0.0, n_regions: float = 0.0, sum_m2: float = 0.0) -> float:
+    return (COST_PER_M3 * float(sum_m3) + COST_PER_M2 * float(sum_m2) + COST_PER_POINT * float(n_points) +
+            COST_PER_REGION * float(n_regions))
 
 
 def lpt_assignment(costs: Sequence[float], world: int) -> List[List[int]]:

@@ -16,7 +16,7 @@ dev = torch.device("cuda:0")
 eng = get_engine(dev)
 lib = _lib.load()
 stream = torch.cuda.current_stream(dev).cuda_stream
-scenes = [to_scene_inputs(inp, dev, noise_seed=i) for i, inp in enumerate(bench.make_inputs(0, 8, "c3"))]
+scenes = [to_scene_inputs(inp, dev, noise_seed=i) for i, inp in enumerate(bench.make_input(i, "c3") for i in range(8))]
 flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 flush = lambda: flush_buf.zero_()
 for mult in (1, 8):
