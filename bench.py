@@ -312,6 +312,23 @@ _RESULT_OUT = sys.stdout
 PHASE_ID = {"A": 2, "B": 3, "GA": 5, "GT": 6, "GC": 8, "GL": 9, "Y": 11, "GK": 12}
 
 
+def morton_order(scene):
+    """The same scene with its points re-ordered along a Morton (Z-order) curve of xyz - the locality a real scan's
+    mesh-vertex order has and the fully shuffled synthetic points lack.  Input plumbing only (torch index ops)."""
+    from gapro_b200.engine import SceneInputs
+    xyz = scene.coords_float
+    lo, hi = xyz.min(0)[0], xyz.max(0)[0]
+    q = ((xyz - lo) / (hi - lo).clamp_min(1e-9) * 1023.0).long().clamp_(0, 1023)
+    code = torch.zeros(xyz.shape[0], dtype=torch.int64, device=xyz.device)
+    for b in range(10):
+        for d in range(3):
+            code |= ((q[:, d] >> b) & 1) << (3 * b + d)
+    order = torch.argsort(code)
+    return SceneInputs(xyz[order].contiguous(), scene.mask_feats[order].contiguous(), scene.spp[order].contiguous(),
+                       scene.instance_cls, scene.instance_box, scene.instance_box_volume, scene.wall_box,
+                       scene.wall_box_volume, noise_seed=scene.noise_seed)
+
+
 def ncu_traffic(kernel_regex, args):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` capture (profiles/r02_traffic.json, written by profiles/summarize.py); null when there is no
@@ -528,6 +545,11 @@ def run_gpu(args):
     stages_large = stage_rooflines(eng, lib, stream, flush)
     for v in stages_large.values():
         v["points"] = eng.last["N"]
+    # ... and on the same points in a spatially coherent order (Morton curve), the order of a real scan's vertices
+    eng.run([morton_order(sc) for sc in passes[0]] * 8, stages_only=True, **kw)
+    stages_morton = stage_rooflines(eng, lib, stream, flush)
+    for v in stages_morton.values():
+        v["points"] = eng.last["N"]
     eng.last = None
 
     # ---- single-scene latency through the reference's per-scene call (BASELINE configs[1]) ---------
@@ -584,6 +606,7 @@ def run_gpu(args):
                 "ms_per_step": ms_e2e, "steps": e2e_steps},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks, "roofline": roofline, "stage_rooflines": stages, "stage_rooflines_large_batch": stages_large,
+        "stage_rooflines_large_batch_morton_order": stages_morton,
         "latency": latency, "cpu_baseline": cpu,
     }
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
