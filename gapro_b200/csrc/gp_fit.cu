@@ -2223,7 +2223,10 @@ static int run_regions(const float* feats_spp, int32_t D, std::vector<Region>& a
             }
         }
         prof_end(stream);
-        for (const Region& r : chunk) prof_account_train(r, iters);
+        for (int g = 0; g < G; ++g) {      // flops of the batched tile kernels: not the regions k_small_fit trains
+            const size_t n_batched = groups[g].size() - (size_t)drv[g].tb.n_small;
+            for (size_t i = 0; i < n_batched; ++i) prof_account_train(groups[g][i], iters);
+        }
         for (int it = 1; it <= iters; ++it)
             for (int g = 0; g < G; ++g) {
                 g_prof_group = g;
