@@ -747,3 +747,33 @@ def test_small_region_kernel_against_numpy_mirror_and_batched_path(dev, lib, mon
         assert rel_err(small[6].cpu().numpy(), tiled[6].cpu().numpy()) < 1e-7
         o = G.fit_region_autograd(X, n1, Xt, noise)
         assert rel_err(small[5].cpu().numpy(), o["mu64"]) < TOL and rel_err(small[6].cpu().numpy(), o["var64"]) < TOL
+
+
+@pytest.mark.parametrize("tcgen05", ["1", "0"])
+def test_heavy_overlap_scene_matches_offline_oracle_fixture(engine, dev, tcgen05, monkeypatch):
+    """A whole configs[3] scene (400k points, 85 boxes, 201 GP regions up to M = 5122 + 2746 test superpoints) against
+    the fp64-oracle fixture (10 CPU-minutes, tests/golden/make_golden_fullsize.py c4): every label bit-exact, posterior
+    mean / variance 1e-5 of their scale (measured 8e-7), with the large regions on tcgen05 digit planes (default) and
+    on the FP64 DMMA path."""
+    from gapro_b200.engine import SceneInputs
+    from tests.golden.make_golden_fullsize import SCENES, input_digest, scene_args
+    monkeypatch.setenv("GAPRO_GP_OZAKI", tcgen05)
+    gold = np.load(os.path.join(GOLD_DIR, "scene_c4_full.npz"))
+    cfg_name, seed, nseed = SCENES["c4"]
+    args = scene_args(cfg_name, seed)
+    assert input_digest(args) == str(gold["digest"])
+    T = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+    sc = SceneInputs(T(args[0], torch.float64), T(args[1], torch.float32), T(args[2], torch.int64), T(args[3], torch.int64),
+                     T(args[4], torch.float32), T(args[5], torch.float32), T(args[6], torch.float32),
+                     T(args[7], torch.float32), noise_seed=nseed)
+    out = engine.run([sc], thresh_spp_occu=0.999)[0]
+    assert engine.last_stats["n_regions"] == int(gold["n_regions"]) and int(gold["max_m"]) > 5000
+    sem, inst, prob, mu, var = [t.cpu().numpy() for t in out]
+    assert float(gold["min_margin"]) > 1e-4             # no label of this scene is decided inside the epsilon band
+    assert (sem == gold["sem"]).all() and (inst == gold["inst"]).all()
+    g = gold["mu"] != -100
+    assert ((mu != -100) == g).all() and ((var != -100) == g).all()
+    assert rel_err(mu[g], gold["mu"][g]) < 1e-5 and rel_err(var[g], gold["var"][g]) < 1e-5
+    assert np.allclose(mu[g], gold["mu"][g], rtol=1e-4, atol=1e-5 * np.abs(gold["mu"][g]).max())
+    assert np.allclose(var[g], gold["var"][g], rtol=1e-4, atol=1e-5 * np.abs(gold["var"][g]).max())
+    assert np.abs(prob - gold["prob"]).max() < 2e-6
