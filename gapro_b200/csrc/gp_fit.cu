@@ -1162,23 +1162,18 @@ k_kgrad(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpPara
 // before the MMAs of the current one.  The squared distance for the lengthscale gradient is recovered from the stored
 // kernel value, r^2 = -2 ln(K / s).
 template <int NCH>
-constexpr int kgrad_wide_smem() { return (2 * 64 * 36 + 2 * 32 * (32 * NCH + 12) + 3 * 64) * (int)sizeof(double); }
+constexpr int kgrad_wide_smem() { return (2 * 64 * 36 + 2 * 32 * (32 * NCH + 4) + 64) * (int)sizeof(double); }
 
 template <int NCH>
 __global__ void __launch_bounds__(256)
 k_kgrad_wide(const Region* __restrict__ regs, const int2* __restrict__ rtiles, GpParams prm, double* __restrict__ ws) {
-    // feature columns 0 .. DP-1, column DP = |row|^2 (so that the lengthscale gradient needs no distance and no log:
-    // sum_j w_ij r_ij^2 = |z_i|^2 sum_j w_ij + sum_j w_ij |y_j|^2 - 2 z_i . sum_j w_ij y_j, all of them outputs of the
-    // same contraction), one more block of 8 columns for it
-    constexpr int DP = 32 * NCH, LDW = 36, LDF = DP + 12, NCB = DP / 8 + 1;
+    constexpr int DP = 32 * NCH, LDW = 36, LDF = DP + 4, NCB = DP / 8;
     extern __shared__ __align__(16) double smem_kw[];
     double* Wz = smem_kw;                               // weight blocks [64 rows][32 columns of the chunk]
     double* Wx = Wz + 64 * LDW;
-    double* Zs = Wx + 64 * LDW;                         // rows jb .. jb+31 of Z and X, [32][D | norm]
+    double* Zs = Wx + 64 * LDW;                         // rows jb .. jb+31 of Z and X, [32][D]
     double* Xs = Zs + 32 * LDF;
-    double* s_sz = Xs + 32 * LDF;                       // per row of the CTA: sum_j W_zz, sum_j W_zx, |z_i|^2
-    double* s_sx = s_sz + 64;
-    double* s_n = s_sx + 64;
+    double* s_cz = Xs + 32 * LDF;
     const int2 rt = rtiles[blockIdx.x];
     const Region R = regs[rt.x];
     const int D = prm.D, M = R.M;
@@ -1192,15 +1187,6 @@ k_kgrad_wide(const Region* __restrict__ regs, const int2* __restrict__ rtiles, G
     const double* X = base + lay.X;
     const int row0 = rt.y * TB;
     if (row0 >= M) return;
-    if (tid < 64) {
-        double n = 0.0;
-        if (row0 + tid < M)
-            for (int d = 0; d < D; ++d) {
-                const double v = Z[(size_t)(row0 + tid) * D + d];
-                n = fma(v, v, n);
-            }
-        s_n[tid] = n;
-    }
     // element-wise role: row er, columns 8 * eq .. 8 * eq + 7 of the chunk
     const int er = tid >> 2, eq = tid & 3;
     const int i = row0 + er;
@@ -1218,10 +1204,10 @@ k_kgrad_wide(const Region* __restrict__ regs, const int2* __restrict__ rtiles, G
             pre[3][u] = *reinterpret_cast<const double2*>(g_kx + jb + 2 * u);
         }
     };
-    double accz[NCB][2], accx[NCB][2];
+    double acc[NCB][2];
 #pragma unroll
-    for (int c = 0; c < NCB; ++c) accz[c][0] = accz[c][1] = accx[c][0] = accx[c][1] = 0.0;
-    double as = 0.0, sz = 0.0, sx = 0.0;
+    for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
+    double as = 0.0, al = 0.0, cz = 0.0;
     const int nblk = (M + 31) >> 5;
     fetch(0);
     for (int b = 0; b < nblk; ++b) {
@@ -1247,8 +1233,10 @@ k_kgrad_wide(const Region* __restrict__ regs, const int2* __restrict__ rtiles, G
                     wz = -gk * kz;
                     wx = -0.5 * gc * kx;
                     as += (gk * kz + gc * kx) * inv_s;
-                    sz += wz;
-                    sx += wx;
+                    cz += wz + wx;
+                    const double r2z = kz > 0.0 ? -2.0 * log(kz * inv_s) : 0.0;     // r^2 (already divided by l^2)
+                    const double r2x = kx > 0.0 ? -2.0 * log(kx * inv_s) : 0.0;
+                    al += (0.5 * wz * r2z + wx * r2x) * m2_ell;
                 }
                 Wz[er * LDW + 8 * eq + 2 * u + h] = wz;
                 Wx[er * LDW + 8 * eq + 2 * u + h] = wx;
@@ -1256,24 +1244,14 @@ k_kgrad_wide(const Region* __restrict__ regs, const int2* __restrict__ rtiles, G
         }
         if (b + 1 < nblk) fetch(jb + 32);
         __syncthreads();
-        // squared norms of the chunk's rows into column DP (columns DP+1 .. DP+7 are zero)
-        if (tid < 64) {
-            double* rowp = (tid < 32 ? Zs : Xs) + (tid & 31) * LDF;
-            double n = 0.0;
-            for (int d = 0; d < D; ++d) n = fma(rowp[d], rowp[d], n);
-            rowp[DP] = n;
-#pragma unroll
-            for (int d = 1; d < 8; ++d) rowp[DP + d] = 0.0;
-        }
-        __syncthreads();
-        // acc(rows 8 warp + gid, feature columns | norm column) += Wz * Zs  and  Wx * Xs
+        // acc(rows 8 warp + gid, feature columns) += Wz * Zs + Wx * Xs
 #pragma unroll
         for (int k0 = 0; k0 < 32; k0 += 4) {
             const double az_ = Wz[(8 * warp + gid) * LDW + k0 + tig], ax_ = Wx[(8 * warp + gid) * LDW + k0 + tig];
 #pragma unroll
             for (int c = 0; c < NCB; ++c) {
-                dmma(accz[c][0], accz[c][1], az_, Zs[(k0 + tig) * LDF + 8 * c + gid]);
-                dmma(accx[c][0], accx[c][1], ax_, Xs[(k0 + tig) * LDF + 8 * c + gid]);
+                dmma(acc[c][0], acc[c][1], az_, Zs[(k0 + tig) * LDF + 8 * c + gid]);
+                dmma(acc[c][0], acc[c][1], ax_, Xs[(k0 + tig) * LDF + 8 * c + gid]);
             }
         }
     }
@@ -1281,42 +1259,28 @@ k_kgrad_wide(const Region* __restrict__ regs, const int2* __restrict__ rtiles, G
 #pragma unroll
     for (int o = 1; o < 4; o <<= 1) {
         as += __shfl_xor_sync(0xffffffffu, as, o);
-        sz += __shfl_xor_sync(0xffffffffu, sz, o);
-        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        al += __shfl_xor_sync(0xffffffffu, al, o);
+        cz += __shfl_xor_sync(0xffffffffu, cz, o);
     }
     if (eq == 0) {
-        s_sz[er] = sz;
-        s_sx[er] = sx;
-        if (i < M) base[lay.gsrow + i] = as;
+        s_cz[er] = cz;
+        if (i < M) {
+            base[lay.gsrow + i] = as;
+            base[lay.glrow + i] = al;
+        }
     }
     __syncthreads();
-    // this lane holds row 8 warp + gid, columns 8 c + 2 tig + {0, 1} of P_z = W_zz Z and P_x = W_zx X
-    const int lr = 8 * warp + gid, oi = row0 + lr;
-    const double szi = s_sz[lr], sxi = s_sx[lr], ni = s_n[lr];
-    double dotz = 0.0, dotx = 0.0;
+    // dZ[i][d] = 2 / l^2 * (cz_i z_i[d] - acc): this lane holds row 8 warp + gid, columns 8 c + 2 tig + {0, 1}
+    const int oi = row0 + 8 * warp + gid;
+    if (oi < M) {
+        const double czi = s_cz[8 * warp + gid];
 #pragma unroll
-    for (int c = 0; c < NCB - 1; ++c)
+        for (int c = 0; c < NCB; ++c)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int d = 8 * c + 2 * tig + e;
-            if (d < D && oi < M) {
-                const double zi = Z[(size_t)oi * D + d];
-                dotz = fma(zi, accz[c][e], dotz);
-                dotx = fma(zi, accx[c][e], dotx);
-                // dZ[i][d] = 2 / l^2 * ((sum_j w_ij) z_i[d] - P_z[i][d] - P_x[i][d])
-                base[lay.gZ + (size_t)oi * D + d] = 2.0 * inv_l2 * fma(szi + sxi, zi, -(accz[c][e] + accx[c][e]));
+            for (int e = 0; e < 2; ++e) {
+                const int d = 8 * c + 2 * tig + e;
+                if (d < D) base[lay.gZ + (size_t)oi * D + d] = 2.0 * inv_l2 * fma(czi, Z[(size_t)oi * D + d], -acc[c][e]);
             }
-        }
-#pragma unroll
-    for (int o = 1; o < 4; o <<= 1) {
-        dotz += __shfl_xor_sync(0xffffffffu, dotz, o);
-        dotx += __shfl_xor_sync(0xffffffffu, dotx, o);
-    }
-    if (tig == 0 && oi < M) {
-        // sum_j w_ij d_ij^2 for both kernels (the norm column is column 0 of the last block: tig 0, e 0)
-        const double qz = ni * szi + accz[NCB - 1][0] - 2.0 * dotz;
-        const double qx = ni * sxi + accx[NCB - 1][0] - 2.0 * dotx;
-        base[lay.glrow + oi] = (0.5 * qz + qx) * (inv_l2 * m2_ell);
     }
 }
 
