@@ -9,7 +9,9 @@ committed rather than recomputed by the GPU tests):
   scene_c4_full.npz    one configs[3] scene (400k points, 85 boxes, 201 GP regions, the largest with M = 5122
                        training and 2746 test superpoints)
 
-    python tests/golden/make_golden_fullsize.py [gp8k] [c1] [c3] [c4]
+  scene_c5_full.npz    one configs[4] scene (1M points, 125 boxes, 349 GP regions up to M = 3587; ~3 CPU-hours)
+
+    python tests/golden/make_golden_fullsize.py [gp8k] [c1] [c3] [c4] [c5]
 
 Like make_golden.py these pin the CUDA path to the ORACLE at full size; the oracle's scene pipeline is
 pinned to the reference's own code by make_ref_golden.py, the inside of the GP fit is a restatement
@@ -31,7 +33,7 @@ from oracle import gp_oracle as G                      # noqa: E402
 from tests.golden.make_golden import gp_case, input_digest   # noqa: E402
 
 GP_8K = (300, 4200, 6, 3800)        # (case id, M, D, N)
-SCENES = {"c1": ("c1", 1000, 11), "c3": ("c3:0", 1000, 12), "c4": ("c4", 1000, 13)}     # name -> (config, scene seed, noise seed)
+SCENES = {"c1": ("c1", 1000, 11), "c3": ("c3:0", 1000, 12), "c4": ("c4", 1000, 13), "c5": ("c5", 1000, 14)}     # name -> (config, scene seed, noise seed)
 
 
 def scene_cfg(name):
