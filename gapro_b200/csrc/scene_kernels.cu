@@ -786,26 +786,22 @@ __global__ void __launch_bounds__(32 * POOL_WARPS)
 k_pool_feats(const float* __restrict__ feats, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg_off,
              int s_total, int D_, float* __restrict__ out) {
     const int D = DT > 0 ? DT : D_;
-    extern __shared__ float pool_smem[];               // [POOL_WARPS][64 * D]
+    extern __shared__ float pool_smem[];               // [POOL_WARPS][32 * D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = blockIdx.x * POOL_WARPS + warp;
     if (g >= s_total) return;
-    float* stage = pool_smem + (size_t)warp * 64 * D;
+    float* stage = pool_smem + (size_t)warp * 32 * D;
     const int start = seg_off[g], end = seg_off[g + 1];
     float acc[2] = {0.0f, 0.0f};                       // lane handles dims lane and lane + 32 (D <= 64)
-    // 64 points per round: a superpoint of the ScanNet-shaped scenes has ~33 points, so that its gathers are ONE
-    // round of independent loads behind the permutation read instead of two dependent rounds
-    for (int base = start; base < end; base += 64) {
-        const int n = min(64, end - base);
-        const int myp0 = (lane < n) ? perm[base + lane] : 0;
-        const int myp1 = (32 + lane < n) ? perm[base + 32 + lane] : 0;
+    for (int base = start; base < end; base += 32) {
+        const int n = min(32, end - base);
+        const int myp = (lane < n) ? perm[base + lane] : 0;
         const int total = n * D;
         for (int e0 = 0; e0 < total; e0 += 32) {           // warp-uniform trip count (full-mask shuffles)
             const int e = e0 + lane;
             const int ec = min(e, total - 1);
             const int pt = ec / D, d = ec - pt * D;
-            const int p0 = __shfl_sync(FULL_MASK, myp0, pt & 31), p1 = __shfl_sync(FULL_MASK, myp1, pt & 31);
-            const int p = pt < 32 ? p0 : p1;
+            const int p = __shfl_sync(FULL_MASK, myp, pt);
             if (e < total) stage[e] = feats[(int64_t)p * D + d];
         }
         __syncwarp();
@@ -834,15 +830,11 @@ extern "C" int gapro_pool_feats(const float* feats, const int32_t* perm, const i
     GAPRO_REQUIRE(feats && perm && seg_off && out, "gapro_pool_feats: null pointer");
     GAPRO_REQUIRE(s_total > 0 && D > 0, "gapro_pool_feats: empty input");
     GAPRO_REQUIRE(D <= 64, "gapro_pool_feats: feature dimension %d > 64", D);
-    const size_t smem = (size_t)POOL_WARPS * 64 * D * sizeof(float);
-    static bool attr_dev[64] = {};
-    int dev = 0;
-    GAPRO_CUDA_TRY(cudaGetDevice(&dev));
-    if (!attr_dev[dev & 63]) {      // up to 8 warps x 64 points x 64 floats = 128 KB
-        GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_pool_feats<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-        GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_pool_feats<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-        GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_pool_feats<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-        attr_dev[dev & 63] = true;
+    const size_t smem = (size_t)POOL_WARPS * 32 * D * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        GAPRO_CUDA_TRY(cudaFuncSetAttribute(k_pool_feats<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
     }
     const unsigned grid = (unsigned)((s_total + POOL_WARPS - 1) / POOL_WARPS);
     if (D == 6)
