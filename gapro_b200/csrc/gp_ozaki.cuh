@@ -287,18 +287,31 @@ k_oz_gemm_b(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpP
                 for (int j = 0; j < 16; ++j) out[j] = mi * gmu[j] + 2.0 * gv[j] * (acc[j] - Am[j]);
             } else if (PH == PH_GT) {        // dT = tril(2 A diag(g_v) B^T + (T - diag(1/T_ii))/N), Adam on T
                 const double invN = 1.0 / (double)M;
+                if (gr < M) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int cc = gc0 + j;
-                    if (gr < M && cc <= gr) {
+                    for (int j = 0; j < 16; j += 2) {
+                        const int cc = gc0 + j;
                         const size_t idx = (size_t)gr * Mp + cc;
-                        double p = base[lay.T + idx];
-                        const double g = 2.0 * acc[j] + (p - (cc == gr ? 1.0 / p : 0.0)) * invN;
-                        double m1 = base[lay.Tm + idx], m2 = base[lay.Tv + idx];
-                        adam_update(p, m1, m2, g, prm);
-                        base[lay.T + idx] = p;
-                        base[lay.Tm + idx] = m1;
-                        base[lay.Tv + idx] = m2;
+                        if (cc + 1 <= gr) {          // both elements in the lower triangle: 128-bit loads / stores
+                            double2 p = *reinterpret_cast<const double2*>(base + lay.T + idx);
+                            double2 m1 = *reinterpret_cast<const double2*>(base + lay.Tm + idx);
+                            double2 m2 = *reinterpret_cast<const double2*>(base + lay.Tv + idx);
+                            const double ga = 2.0 * acc[j] + p.x * invN;
+                            const double gb = 2.0 * acc[j + 1] + (p.y - (cc + 1 == gr ? 1.0 / p.y : 0.0)) * invN;
+                            adam_update(p.x, m1.x, m2.x, ga, prm);
+                            adam_update(p.y, m1.y, m2.y, gb, prm);
+                            *reinterpret_cast<double2*>(base + lay.T + idx) = p;
+                            *reinterpret_cast<double2*>(base + lay.Tm + idx) = m1;
+                            *reinterpret_cast<double2*>(base + lay.Tv + idx) = m2;
+                        } else if (cc == gr) {       // the diagonal element alone
+                            double p = base[lay.T + idx];
+                            const double g = 2.0 * acc[j] + (p - 1.0 / p) * invN;
+                            double m1 = base[lay.Tm + idx], m2 = base[lay.Tv + idx];
+                            adam_update(p, m1, m2, g, prm);
+                            base[lay.T + idx] = p;
+                            base[lay.Tm + idx] = m1;
+                            base[lay.Tv + idx] = m2;
+                        }
                     }
                 }
             } else if (PH == PH_GC || PH == PH_Y) {
