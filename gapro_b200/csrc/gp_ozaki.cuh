@@ -278,13 +278,16 @@ k_oz_gemm_b(const Region* __restrict__ regs, const int4* __restrict__ tiles, GpP
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(out + j) = make_double2(acc[j], acc[j + 1]);
             } else if (PH == PH_GA) {        // G_A = m g_mu^T + 2 (T B - A) diag(g_v)
-                const double* Am = base + lay.A + (size_t)gr * Wp + gc0;
+                const double2* Am = reinterpret_cast<const double2*>(base + lay.A + (size_t)gr * Wp + gc0);
                 const double mi = base[lay.m + gr];
-                const double* gmu = base + lay.gmu + gc0;
-                const double* gv = base + lay.gv + gc0;
-                double* out = base + lay.GA + (size_t)gr * Mp + gc0;
+                const double2* gmu = reinterpret_cast<const double2*>(base + lay.gmu + gc0);
+                const double2* gv = reinterpret_cast<const double2*>(base + lay.gv + gc0);
+                double2* out = reinterpret_cast<double2*>(base + lay.GA + (size_t)gr * Mp + gc0);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) out[j] = mi * gmu[j] + 2.0 * gv[j] * (acc[j] - Am[j]);
+                for (int j = 0; j < 8; ++j) {
+                    const double2 a = Am[j], u = gmu[j], w = gv[j];
+                    out[j] = make_double2(mi * u.x + 2.0 * w.x * (acc[2 * j] - a.x), mi * u.y + 2.0 * w.y * (acc[2 * j + 1] - a.y));
+                }
             } else if (PH == PH_GT) {        // dT = tril(2 A diag(g_v) B^T + (T - diag(1/T_ii))/N), Adam on T
                 const double invN = 1.0 / (double)M;
                 if (gr < M) {
