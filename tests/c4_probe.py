@@ -14,8 +14,9 @@ from tests.conftest import rel_err  # noqa: E402
 from tests.golden.make_golden_fullsize import SCENES, scene_args  # noqa: E402
 
 dev = torch.device("cuda:0")
-gold = np.load(os.path.join(ROOT, "tests", "golden", "scene_c4_full.npz"))
-cfg_name, seed, nseed = SCENES["c4"]
+TAG = sys.argv[1] if len(sys.argv) > 1 else "c4"
+gold = np.load(os.path.join(ROOT, "tests", "golden", f"scene_{TAG}_full.npz"))
+cfg_name, seed, nseed = SCENES[TAG]
 args = scene_args(cfg_name, seed)
 T = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
 sc = SceneInputs(T(args[0], torch.float64), T(args[1], torch.float32), T(args[2], torch.int64), T(args[3], torch.int64),
@@ -36,3 +37,9 @@ for oz in ("0", "1"):
           f"mu rel {rel_err(mu[g], gold['mu'][g]):.2e} var rel {rel_err(var[g], gold['var'][g]):.2e} "
           f"prob max abs {np.abs(prob - gold['prob']).max():.2e}; elementwise mu rtol max "
           f"{np.max(np.abs(mu[g] - gold['mu'][g]) / np.abs(gold['mu'][g])):.2e}", flush=True)
+    bad = np.flatnonzero((sem != gold["sem"]) | (inst != gold["inst"]))
+    if len(bad):
+        print("   first differing points:", bad[:5], "prob there", prob[bad[:5]], "oracle prob", gold["prob"][bad[:5]],
+              "n_regions", eng.last_stats["n_regions"], int(gold["n_regions"]))
+    k = np.argsort(-np.abs(mu[g] - gold["mu"][g]))[:3]
+    print("   worst mu:", mu[g][k], gold["mu"][g][k], "var:", var[g][k], gold["var"][g][k])
