@@ -289,7 +289,9 @@ class GaproEngine:
             if cap is None:
                 free, _ = torch.cuda.mem_get_info(dev)
                 held = self._ws.get("gp")
-                cap = int(0.7 * (free + (held.numel() if held is not None else 0)))
+                held_bytes = held.numel() if held is not None else 0
+                del held            # no alias may survive into _workspace(): growing frees the old buffer first
+                cap = int(0.7 * (free + held_bytes))
             nbytes = max(min(full, cap), need)
             ws = self._workspace("gp", nbytes)
             train_idx_ptr = lists_idx.data_ptr() + 4 * n_inter_total
