@@ -1376,11 +1376,13 @@ static int oz_digits() {
     return s < 5 ? 5 : (s > 8 ? 8 : s);
 }
 static int oz_min_rows() {
-    // Regions with at least this many padded training rows run their tile products on tcgen05 (8 digits: the same
-    // 1e-6 parity bar as the DMMA path on the 8k-superpoint golden region, 1.27x faster on the configs[3] / configs[4]
-    // workloads; below ~2000 rows the slicing passes eat the gain - DESIGN.md section 4.1).  GAPRO_GP_OZAKI=0 turns
-    // the path off, GAPRO_GP_OZAKI_MIN_M moves the threshold.
-    int on = 1, m = 2048;
+    // GAPRO_GP_OZAKI=1: regions with at least this many padded training rows run their tile products on tcgen05
+    // (8 digits).  Opt-in: the digit-plane products are accurate relative to row-max x column-max x K, float64 is
+    // accurate componentwise, and the 50-step Adam trajectory amplifies the difference.  Measured against the fp64
+    // oracle: 4.4e-7 on the 8k-superpoint golden region and 8e-7 on the whole configs[3] scene (same as DMMA, 1.28x
+    // faster), but 7.8e-5 (worst element 1.6e-4) on the worst-conditioned region of the configs[4] scene, where DMMA
+    // itself is at 8e-6 - past the 1e-4 bar, so it is not the default.
+    int on = 0, m = 2048;
     if (const char* e = getenv("GAPRO_GP_OZAKI")) on = atoi(e);
     if (const char* e = getenv("GAPRO_GP_OZAKI_MIN_M")) m = atoi(e);
     return on ? m : (1 << 30);
